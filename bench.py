@@ -1,0 +1,460 @@
+#!/usr/bin/env python3
+"""bench.py -- beam power maps/s (and DAS GMAC/s) of the time-domain delay-and-sum hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--algo pad|lerp] [--frames F] [--workload c3|c1|stock]
+
+Workload (config.workload): BASELINE config C3 -- 4 arrays / 256 microphones, 256-sample
+buffers, 180x180 direction grid (D = 32 400), time-domain DAS power map, synthetic 3-source
+input.  C3 is the configuration BASELINE.json's metric "beam power maps/s" is
+quoted on and it fits one GPU; configs[1] (MISO) is measured as the extra "miso" object.
+
+A *step* is one pass of the hot path over one batch of F frames (F maps).  Inputs are resident
+in HBM before the timed region; every step reads a different batch out of a pool larger than
+the 126 MB L2 ("inputs larger than L2").  With N > 1 ranks (torchrun) the direction grid is
+sharded: each rank computes D/N directions of all F maps and ONE in-place NCCL all-gather per
+step assembles the direction-major maps on every rank -> total work fixed -> "strong".
+
+value      whole-job maps/s, device-timed (CUDA events, max over ranks)
+e2e        maps/s through the reference-facing C-ABI call mimo_pad()/mimo_lerp() with HOST
+           buffers (H2D + D2H inside the timed region), each rank serving its own frames
+roofline   dominant kernel (das_mimo_kernel) vs the measured HBM copy bandwidth
+cpu_baseline  the reference's own C (oracle/_ref) or the oracle port on the host cores
+--impl reference   the reference CPU implementation alone, same metric/config
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "zybo-rt-sampler-image-detection_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    "c3": dict(N_MICROPHONES=256, N_SAMPLES=256, MAX_RES_X=180, MAX_RES_Y=180, GEOMETRY_N_MICS=256,
+               GEOMETRY_N_ARRAYS=4, ref_cfg="c3",
+               desc="C3: 256 mics (4 arrays), 256-sample buffers @48.828 kHz, 180x180 grid, TD-DAS power map"),
+    "c1": dict(N_MICROPHONES=64, N_SAMPLES=256, MAX_RES_X=20, MAX_RES_Y=20, GEOMETRY_N_MICS=64,
+               GEOMETRY_N_ARRAYS=1, ref_cfg="c1",
+               desc="C1: 64 mics (8x8), 256-sample buffers, 20x20 grid, TD-DAS power map"),
+    "stock": dict(N_MICROPHONES=256, N_SAMPLES=256, MAX_RES_X=57, MAX_RES_Y=32, GEOMETRY_N_MICS=256,
+                  GEOMETRY_N_ARRAYS=4, ref_cfg="default",
+                  desc="stock config.json: 256 mics, 256 samples, 57x32 grid, TD-DAS power map"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------
+# CPU side: the reference's own C (oracle/_ref) or the oracle port, one process per core
+# ----------------------------------------------------------------------------------------
+_BARRIER = None          # inherited by the forked workers (cannot be pickled)
+
+
+def _cpu_worker(args):
+    kind, ref_cfg, algo, sig, mics, table, D, maps = args
+    barrier = _BARRIER
+    if kind == "reference":
+        from oracle import ref
+        R = ref.RefC(ref_cfg)
+        import ctypes
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        img = np.zeros(R.D, np.float32)
+        if algo == "pad":
+            R.L.load_coefficients_pad(p(table), ctypes.c_int(table.size))
+            fn = R.L.mimo_pad
+        else:
+            R.L.load_coefficients_lerp(p(table), ctypes.c_int(table.size))
+            fn = R.L.mimo_lerp
+        call = lambda: fn(p(sig), p(img), p(mics), ctypes.c_int(len(mics)))
+    else:
+        from oracle import cpu
+        if algo == "pad":
+            call = lambda: cpu.mimo_pad(sig, mics, table, D)
+        else:
+            call = lambda: cpu.mimo_lerp(sig, mics, table, D)
+    call()                                   # warm-up map (page-in, table load)
+    barrier.wait()
+    t0 = time.perf_counter()
+    for _ in range(maps):
+        call()
+    return time.perf_counter() - t0
+
+
+def cpu_setup(wl_name, algo):
+    """Inputs of the CPU run, from the oracle's NumPy restatement of the delay generator."""
+    from oracle import directions_np as dn, ref
+    from lib import synthetic
+    wl = WORKLOADS[wl_name]
+    cfg = dn.cfg_with(N_MICROPHONES=wl["N_MICROPHONES"], MAX_RES_X=wl["MAX_RES_X"],
+                      MAX_RES_Y=wl["MAX_RES_Y"], n_mics_geom=wl["GEOMETRY_N_MICS"],
+                      n_arrays_geom=wl["GEOMETRY_N_ARRAYS"])
+    mics, n = dn.active_microphones(cfg)
+    delays = dn.calculate_delays(cfg).reshape(-1, n)
+    D = delays.shape[0]
+    src = synthetic.C3 if wl_name == "c3" else synthetic.C1
+    sources = [s for s in src["sources"] if s[0] < D]
+    sig = synthetic.point_sources(delays, mics, wl["N_MICROPHONES"], wl["N_SAMPLES"], 48828.0,
+                                  sources, src["noise"], src["seed"])
+    table = delays.astype(int).astype(np.int32) if algo == "pad" else np.float32(delays)
+    kind = "reference" if ref.available(wl["ref_cfg"]) else "port"
+    return kind, wl["ref_cfg"], sig, np.ascontiguousarray(mics, np.int32), np.ascontiguousarray(table), D, n
+
+
+def cpu_run(wl_name, algo, maps_per_core, cores=None, setup=None):
+    """maps/s of the CPU implementation with `cores` processes, each producing whole maps
+    (the reference is single-threaded with process-global tables)."""
+    kind, ref_cfg, sig, mics, table, D, n = setup or cpu_setup(wl_name, algo)
+    cores = cores or os.cpu_count() or 1
+    global _BARRIER
+    ctx = mp.get_context("fork")
+    _BARRIER = ctx.Barrier(cores)
+    with ctx.Pool(cores) as pool:
+        times = pool.map(_cpu_worker, [(kind, ref_cfg, algo, sig, mics, table, D, maps_per_core)] * cores,
+                         chunksize=1)
+    wall = max(times)
+    return dict(maps_per_s=cores * maps_per_core / wall, seconds=wall, cores=cores, kind=kind,
+                maps=cores * maps_per_core, D=D, n=n)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path, all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = WORKLOADS[args.workload]
+    setup = cpu_setup(args.workload, args.algo)
+    D, n = setup[5], setup[6]
+    N = wl["N_SAMPLES"]
+    cores = os.cpu_count() or 1
+    # one step = one whole map per core (bounded sample of the F-frame step of the GPU arm)
+    total = 0.0
+    for i in range(args.warmup + args.steps):
+        r = cpu_run(args.workload, args.algo, 1, cores, setup)
+        if i >= args.warmup:
+            total += r["seconds"]
+    kind = r["kind"]
+    maps = cores * args.steps
+    value = maps / total
+    line = {
+        "impl": "reference", "metric": "beam power maps/s", "value": value, "unit": "maps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "gmac_per_s": value * D * n * N / 1e9,
+        "config": {"workload": wl["desc"], "algo": args.algo, "directions": D, "mics": n, "samples": N},
+        "cpu_baseline": {"value": value, "unit": "maps/s", "cores": cores, "kind": kind,
+                         "sample": "%d whole maps per step (one per host core), %d steps" % (cores, args.steps)},
+        "e2e": {"value": value, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------
+# clocks during the timed region
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------
+# the B200 arm
+# ----------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--algo", default="pad", choices=["pad", "lerp"])
+    ap.add_argument("--frames", type=int, default=32, help="maps per step")
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the MISO / e2e extras")
+    ap.add_argument("--exact-sum", type=int, default=1)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+
+    # ---- cpu_baseline first (forks worker processes: before CUDA is initialised) ----------
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        setup = cpu_setup(args.workload, args.algo)
+        cores = os.cpu_count() or 1
+        probe = cpu_run(args.workload, args.algo, 1, cores, setup)
+        maps_per_core = max(1, int(12.0 / max(probe["seconds"], 1e-3)))       # ~12 s of CPU work
+        maps_per_core = min(maps_per_core, 200)
+        r = cpu_run(args.workload, args.algo, maps_per_core, cores, setup)
+        one = cpu_run(args.workload, args.algo, max(1, maps_per_core // 4), 1, setup)
+        cpu_base = {"value": r["maps_per_s"], "unit": "maps/s", "cores": cores, "kind": r["kind"],
+                    "sample": "%d whole %s maps (%d per core, one process per core), %.1f s"
+                              % (r["maps"], args.workload.upper(), maps_per_core, r["seconds"]),
+                    "one_core_maps_per_s": one["maps_per_s"],
+                    "gmac_per_s": r["maps_per_s"] * r["D"] * r["n"] * wl["N_SAMPLES"] / 1e9}
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from interface import config
+    config.reload(N_MICROPHONES=wl["N_MICROPHONES"], N_SAMPLES=wl["N_SAMPLES"], MAX_RES_X=wl["MAX_RES_X"],
+                  MAX_RES_Y=wl["MAX_RES_Y"], N_TAPS=8, SKIP_N_MICS=1,
+                  GEOMETRY_N_MICS=wl["GEOMETRY_N_MICS"], GEOMETRY_N_ARRAYS=wl["GEOMETRY_N_ARRAYS"])
+    from lib import _native as nat, directions, synthetic
+    L = nat.lib()
+    nat.check(L.bf_set_device(local_rank))
+    nat.configure_from(config)
+    L.bf_set_kernel_options(0, args.exact_sum)
+    algo = nat.ALGO_PAD if args.algo == "pad" else nat.ALGO_LERP
+
+    # ---- tables: device generator -> device table, no host round trip ----------------------
+    if args.algo == "pad":
+        directions.load_pad_from_geometry()
+    else:
+        directions.load_lerp_from_geometry()
+    mics, n = directions.active_microphones()
+    mics = nat.i32(mics)
+    M, N = config.N_MICROPHONES, config.N_SAMPLES
+    D = config.MAX_RES_X * config.MAX_RES_Y
+    F = args.frames
+
+    # ---- synthetic inputs: pool of batches larger than L2 ----------------------------------
+    delays = directions.calculate_delays().reshape(-1, n)
+    src = synthetic.C3 if args.workload == "c3" else synthetic.C1
+    sources = [s for s in src["sources"] if s[0] < D]
+    base = synthetic.point_sources(delays, mics, M, N, 48828.0, sources, src["noise"], src["seed"])
+    del delays
+    frame_bytes = M * N * 4
+    pool = max(2, int(np.ceil(160e6 / (F * frame_bytes))))
+    gen = torch.Generator(device="cuda").manual_seed(1236)
+    d_base = torch.from_numpy(base).cuda()
+    d_pool = d_base[None, None] + 0.01 * torch.randn((pool, F, M, N), generator=gen, device="cuda")
+    d_pool = d_pool.contiguous()
+    d_mics = torch.from_numpy(mics).cuda()
+
+    # ---- direction shard of this rank --------------------------------------------------------
+    per = (D + world - 1) // world
+    d_begin = rank * per
+    d_count = max(0, min(per, D - d_begin))
+    if world > 1:
+        d_maps = torch.zeros((per * world, F), device="cuda")    # direction-major, gather in place
+        fs, ds = 1, F
+    else:
+        d_maps = torch.zeros((F, D), device="cuda")
+        fs, ds = D, 1
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(i):
+        sig = d_pool[i % pool]
+        nat.check(L.bf_mimo_dev_ex(algo, sig.data_ptr(), d_maps.data_ptr(), F, d_mics.data_ptr(), n,
+                                   d_begin, d_count, fs, ds, 0, stream))
+        if world > 1:
+            dist.all_gather_into_tensor(d_maps, d_maps[d_begin:d_begin + per])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    L.bf_kernel_launches(1)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        ev[i][0].record()
+        step(args.warmup + i)
+        ev[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = int(L.bf_kernel_launches(0))
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    # whole timed region on the device as well (first start -> last stop)
+    span_ms = ev[0][0].elapsed_time(ev[-1][1])
+    t = torch.tensor([dev_ms, span_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, span_ms = float(t[0]), float(t[1])
+    clocks = sampler.stop() if rank == 0 else None
+    value = F * args.steps / (span_ms * 1e-3)
+
+    # ---- kernel-only time of the dominant kernel for the roofline (rank 0's slice) -----------
+    kt = []
+    for i in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sig = d_pool[(i + 3) % pool]
+        a.record()
+        nat.check(L.bf_mimo_dev_ex(algo, sig.data_ptr(), d_maps.data_ptr(), F, d_mics.data_ptr(), n,
+                                   d_begin, d_count, fs, ds, 0, stream))
+        b.record()
+        torch.cuda.synchronize()
+        kt.append(a.elapsed_time(b))
+    k_ms = float(np.mean(kt))
+    table_bytes = D * n * 4 * (2 if args.algo == "lerp" else 1)
+    map_bytes = frame_bytes + table_bytes + D * 4                 # table every map
+    launch_bytes = F * map_bytes * (d_count / D)
+    hbm_peak, peak_src = peaks()
+    achieved = launch_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("das_mimo_%s_F%d" % (args.algo, F))
+    adds = F * d_count * n * N * (2 if args.algo == "lerp" else 1)
+    fp32_peak = 148 * 128 * (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel": "das_mimo_kernel<%s>" % args.algo, "kernel_ms": k_ms,
+                "algorithmic_bytes_per_launch": launch_bytes,
+                "accounting": "table counted once per map (SURVEY 8d primary); per launch = F maps",
+                "actual_bound": "fp32 issue (FADD2/FFMA2) -- dense maps are ~63 adds/byte, see DESIGN.md",
+                "fp32_lane_ops_per_s": adds / (k_ms * 1e-3),
+                "fp32_frac_of_148x128_lanes": (adds / (k_ms * 1e-3)) / fp32_peak if fp32_peak else None}
+
+    # ---- e2e: the reference-facing call with host buffers -------------------------------------
+    e2e, miso = None, None
+    if not args.no_extras:
+        h_sig = np.ascontiguousarray(base)
+        h_img = np.zeros(D, np.float32)
+        fn = L.mimo_pad if args.algo == "pad" else L.mimo_lerp
+        for _ in range(5):
+            fn(nat.ptr(h_sig), nat.ptr(h_img), nat.ptr(mics), n)
+        nat.check()
+        e2e_maps = max(F, 64)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_maps):
+            fn(nat.ptr(h_sig), nat.ptr(h_img), nat.ptr(mics), n)
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        nat.check()
+        te = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_value = world * e2e_maps / float(te[0])
+        e2e = {"value": e2e_value, "unit": "maps/s",
+               "h2d_bytes_per_step": F * (frame_bytes + n * 4), "d2h_bytes_per_step": F * D * 4,
+               "api": "mimo_%s(signals, image, adaptive_array, n) -- host pointers, one map per call, "
+                      "each rank serves its own frames" % args.algo,
+               "ms_per_map": 1e3 * float(te[0]) / e2e_maps}
+
+        # ---- extra: BASELINE config C2, MISO stream (HBM-bound) ----------------------------
+        if rank == 0:
+            try:
+                blocks = 4096
+                n_m = 64
+                sig_m = torch.randn((blocks, M, N), generator=gen, device="cuda")
+                out_m = torch.zeros((blocks, N), device="cuda")
+                d_m64 = d_mics[:n_m].contiguous()
+                off = (D // 2) * n
+                ts = []
+                for i in range(8):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    nat.check(L.bf_miso_dev(algo, sig_m.data_ptr(), out_m.data_ptr(), blocks, d_m64.data_ptr(),
+                                            n_m, off, 1, stream))
+                    b.record()
+                    torch.cuda.synchronize()
+                    ts.append(a.elapsed_time(b))
+                ms = float(np.mean(ts[3:]))
+                blk_bytes = n_m * N * 4 + 2 * n_m * 4 + N * 4
+                gbs = blocks * blk_bytes / (ms * 1e-3) / 1e9
+                miso = {"workload": "C2: MISO, 64 mics, %d consecutive 256-sample blocks (%.2f GB, > L2), steer row + /n*MIC_GAIN" % (blocks, blocks * M * N * 4 / 1e9),
+                        "samples_per_s": blocks * N / (ms * 1e-3), "x_realtime": blocks * N / (ms * 1e-3) / 48828.0,
+                        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": gbs / hbm_peak, "kernel": "miso_stream_kernel", "kernel_ms": ms,
+                                     "traffic": None}}
+                del sig_m, out_m
+            except Exception as e:  # noqa: BLE001
+                miso = {"error": str(e)}
+
+    if rank == 0:
+        line = {
+            "metric": "beam power maps/s", "value": value, "unit": "maps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": span_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "gmac_per_s": value * D * n * N / 1e9,
+            "config": {"workload": wl["desc"], "algo": args.algo, "frames_per_step": F, "directions": D,
+                       "mics": n, "samples": N, "l2": "inputs larger than L2 (pool of %d batches, %.0f MB)"
+                       % (pool, pool * F * frame_bytes / 1e6),
+                       "parallelism": "directions sharded over %d rank(s)%s" % (
+                           world, ", one in-place NCCL all-gather per step" if world > 1 else ""),
+                       "exact_sum": args.exact_sum},
+            "sum_step_ms": dev_ms, "wall_s": t_wall, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "miso": miso,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

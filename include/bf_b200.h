@@ -1,0 +1,198 @@
+/*
+ * bf_b200.h -- C ABI of libbf_b200.so, the B200 (sm_100a) beamformer.
+ *
+ * Part 1 re-declares, with identical names and signatures, the C functions
+ * that the reference's Cython boundary binds for the beamforming hot path
+ * (PC/src/main.pyx:45-90 `cdef extern`, PC/src/benchmark.pyx:28-55).  A build
+ * of the reference that links this library instead of compiling
+ * PC/src/algorithms/*.c gets the CUDA path with no source change (see
+ * INTEGRATION.md).  Pointer arguments of part 1 are HOST pointers, exactly as
+ * in the reference; each call copies in, runs on the current CUDA device and
+ * copies the result back before returning.
+ *
+ * Part 2 is what the reference cannot express because its sizes are
+ * compile-time macros (PC/src/config.h generated from config.json): run-time
+ * configuration, error reporting, and device-resident / batched / sharded
+ * entry points used by the host layer, bench.py and the multi-GPU path.
+ *
+ * Plain C: pointers and sizes only, no CUDA or torch types.  `stream` arguments
+ * are a cudaStream_t passed as void* (NULL = default stream).
+ *
+ * All file:line citations are relative to /root/reference/PC/src/.
+ */
+#ifndef BF_B200_H
+#define BF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ===================================================================== *
+ *  Part 1 -- drop-in names                                              *
+ * ===================================================================== */
+
+/* ---- algorithms/pad_and_sum.h:5-13 ---------------------------------- */
+void pad_delay(float *signal, float *out, int pos_pad);
+void miso_pad(float *signals, float *out, int *adaptive_array, int n, int offset);
+void miso_pad2(float *signals, float *out, int *adaptive_array, int n, int offset);
+void mimo_pad(float *signals, float *image, int *adaptive_array, int n);
+void load_coefficients_pad(int *whole_samples, int n);
+void load_coefficients_pad2(int *whole_miso, int n);
+void unload_coefficients_pad(void);
+void unload_coefficients_pad2(void);
+
+/* ---- algorithms/lerp_and_sum.h:4-12 --------------------------------- */
+void lerp_delay(float *signal, float *out, float h, int pad);
+void miso_lerp(float *signals, float *out, int *adaptive_array, int n, int offset);
+void mimo_lerp(float *signals, float *image, int *adaptive_array, int n);
+void load_coefficients_lerp(float *delays, int n);
+void unload_coefficients_lerp(void);
+
+/* ---- algorithms/convolve_and_sum.h:4-22 ------------------------------
+ * (convolve_naive is declared there but never defined in the reference; it is
+ * not exported here either.) */
+void convolve_delay_naive_add(float *signal, float *h, float *out);
+void convolve_delay_vectorized(float *signal, float *h, float *out);
+void convolve_delay_vectorized_add(float *signal, float *h, float *out);
+void convolve_delay_naive(float *signal, float *out, float *h);
+void miso_convolve_naive(float *signals, float *out, int *adaptive_array, int n, int offset);
+void mimo_convolve_naive(float *signals, float *image, int *adaptive_array, int n);
+void miso_convolve_vectorized(float *signals, float *out, int *adaptive_array, int n, int offset);
+void mimo_convolve_vectorized(float *signals, float *image, int *adaptive_array, int n);
+void load_coefficients_convolve(float *h, int n);
+void unload_coefficients_convolve(void);
+
+/* ---- algorithms/hybrid_convolve_and_sum.h:4-12 ---------------------- */
+void convolve_hybrid_delay_add(float *signal, float *h, int pad, float *out);
+void miso_convolve_hybrid(float *signals, float *out, int *adaptive_array, int n, int offset);
+void mimo_convolve_hybrid(float *signals, float *image, int *adaptive_array, int n);
+void load_coefficients_convolve_hybrid(float *h, int n);
+void unload_coefficients_convolve_hybrid(void);
+
+/* ---- api.h:11-20 -------------------------------------------------------
+ * In the reference these fetch the latest sample buffer with get_data()
+ * (api.c:830-859, SysV shared memory fed by the UDP receiver, which stays host
+ * C) and then call the kernels above.  Here the buffer comes from the callback
+ * registered with bf_set_data_source(); without one they fail (bf_last_error). */
+void pad_mimo(float *image, int *adaptive_array, int n);
+void lerp_mimo(float *image, int *adaptive_array, int n);
+void convolve_mimo_naive(float *image, int *adaptive_array, int n);
+void convolve_mimo_vectorized(float *image, int *adaptive_array, int n);
+void mimo_truncated(float *image, int *adaptive_array, int n);
+void load_coefficients2(int *whole_samples, int n);
+void miso_steer_listen(float *out, int *adaptive_array, int n, int steer_offset);
+
+/* ===================================================================== *
+ *  Part 2 -- run-time configuration and device-side entry points        *
+ * ===================================================================== */
+
+/* The config.json "general" constants the hot path reads as macros
+ * (config.json:3-21, config.pxd:5-26). */
+typedef struct bf_config {
+    int n_microphones;      /* N_MICROPHONES: rows of the sample buffer        */
+    int n_samples;          /* N_SAMPLES:     samples per row (block length)   */
+    int n_taps;             /* N_TAPS                                          */
+    int max_res_x;          /* MAX_RES_X                                       */
+    int max_res_y;          /* MAX_RES_Y  (D = max_res_x * max_res_y)          */
+    float mic_gain;         /* MIC_GAIN (api.c:519-523 MISO post-scale)        */
+    int fir_fused;          /* -1 auto (n_taps <= 16), 0 mul+add, 1 fma: how the
+                               sequential FIR tap loop rounds, see oracle.c     */
+} bf_config;
+
+enum {
+    BF_OK = 0,
+    BF_ERR_CONFIG = 1,      /* bad size / unsupported configuration            */
+    BF_ERR_NOT_LOADED = 2,  /* coefficient table missing or too small          */
+    BF_ERR_CUDA = 3,        /* CUDA runtime error (text in bf_last_error)      */
+    BF_ERR_ARG = 4          /* bad pointer / range argument                    */
+};
+
+enum {                      /* delay algorithms                                */
+    BF_ALGO_PAD = 0,        /* integer zero-pad delay      (pad_and_sum.c)     */
+    BF_ALGO_LERP = 1,       /* integer + linear interp.    (lerp_and_sum.c)    */
+    BF_ALGO_FIR_SEQ = 2,    /* N_TAPS FIR, sequential taps (convolve naive)    */
+    BF_ALGO_FIR_LANES = 3,  /* N_TAPS FIR, 8-lane AVX order (convolve vector.) */
+    BF_ALGO_HYBRID = 4      /* integer pad + FIR fraction  (hybrid_convolve)   */
+};
+
+int bf_configure(const bf_config *cfg);        /* default = stock config.json   */
+int bf_get_config(bf_config *cfg);
+const char *bf_last_error(void);               /* thread-local, never NULL      */
+int bf_last_status(void);                      /* status of the last part-1 call */
+int bf_device_count(void);
+int bf_set_device(int ordinal);                /* device used by this thread's calls */
+const char *bf_version(void);
+
+/* Source of sample buffers for the api.h wrappers: called with a host pointer
+ * to n_microphones*n_samples floats to fill (same contract as get_data()). */
+typedef void (*bf_data_source_fn)(float *signals);
+void bf_set_data_source(bf_data_source_fn fn);
+
+/* Implementation selector for the power-map kernels: 0 = tiled TMA kernel
+ * (default), 1 = simple one-block-per-direction kernel (any n_samples <= 1024).
+ * exact_sum: 1 = reproduce the reference's in-order sum of squares bit for bit
+ * (default), 0 = warp-shuffle tree (<= 1e-6 relative). */
+int bf_set_kernel_options(int simple_kernel, int exact_sum);
+
+/* ---- device-resident, batched, direction-sharded power maps ----------
+ * d_signals  device float [frames][n_microphones][n_samples]
+ * d_images   device float [frames][D]; only [d_begin, d_begin+d_count) written
+ * d_mic_ids  device int [n]  (adaptive_array: mic id of table column m)
+ * Uses the table loaded for `algo` by the matching load_coefficients_* (or
+ * bf_load_table_dev).  Asynchronous on `stream`. */
+int bf_mimo_dev(int algo, const float *d_signals, float *d_images, int frames,
+                const int *d_mic_ids, int n, int d_begin, int d_count, void *stream);
+
+/* Same, with an explicit output layout: the power of frame f, direction d is stored at
+ *   d_images[f * frame_stride + (d - d_origin) * dir_stride]
+ * bf_mimo_dev == (frame_stride = D, dir_stride = 1, d_origin = 0).  Direction-major maps
+ * (frame_stride = 1, dir_stride = frames) make every rank's direction slice one contiguous
+ * block, so a single in-place NCCL all-gather assembles the sharded map. */
+int bf_mimo_dev_ex(int algo, const float *d_signals, float *d_images, int frames,
+                   const int *d_mic_ids, int n, int d_begin, int d_count, long frame_stride,
+                   long dir_stride, int d_origin, void *stream);
+
+/* ---- device-resident MISO stream (BASELINE config C2) -----------------
+ * d_signals device float [blocks][n_microphones][n_samples]
+ * d_out     device float [blocks][n_samples]
+ * offset    row offset into the table (= direction * n), as in miso_pad
+ * scale     0: raw sum (miso_pad / miso_lerp); 1: out/n*mic_gain (api.c:519-523) */
+int bf_miso_dev(int algo, const float *d_signals, float *d_out, int blocks,
+                const int *d_mic_ids, int n, int offset, int scale, void *stream);
+
+/* ---- tables straight from device memory -------------------------------
+ * algo PAD: d_table = int32 [count]; LERP/HYBRID: float32 delays [count];
+ * FIR_*: float32 taps [count].  Same semantics as load_coefficients_*. */
+int bf_load_table_dev(int algo, const void *d_table, size_t count);
+
+/* ---- delay-table generator (directions.pyx:90-124) --------------------
+ * Host computes the O(X+Y+n) scalars exactly as the reference does; the device
+ * evaluates the D*n table in float64 in the reference's operation order.
+ *   k        (double)((float)fs / (float)c)
+ *   x_scan   double [res_x], y_scan double [res_y]  (np.linspace values)
+ *   z2       (double)powf(z, 2)
+ *   mic_x/y  double [n] coordinates of the active microphones
+ * Outputs (any may be NULL), all HOST pointers, row-major [res_x*res_y][n]:
+ *   delays_f64, whole_i32 (trunc), delays_f32 (round to nearest).
+ * If load_algo >= 0 the generated table is also installed on the device as if
+ * load_coefficients_{pad,lerp,convolve_hybrid} had been called (no host trip). */
+int bf_generate_delays(double k, const double *x_scan, int res_x, const double *y_scan,
+                       int res_y, double z2, const double *mic_x, const double *mic_y, int n,
+                       double *delays_f64, int *whole_i32, float *delays_f32, int load_algo);
+
+/* The lerp split of load_coefficients_lerp (lerp_and_sum.c:139-153) as data:
+ * copies the device-resident tables back (HOST pointers, may be NULL). */
+int bf_get_lerp_tables(int *whole, float *weight, size_t count);
+/* ... and the hybrid split (hybrid_convolve_and_sum.c:161-180). */
+int bf_get_hybrid_tables(int *whole, float *taps, size_t count);
+
+/* Counters for bench.py: kernels launched by this library since the last reset. */
+uint64_t bf_kernel_launches(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BF_B200_H */

@@ -1,0 +1,211 @@
+"""GPU: device-resident, batched and direction-sharded entry points (bf_mimo_dev, bf_miso_dev),
+the MISO stream kernel, the producer loops of lib.beamformer, and size-independent properties at
+the full BASELINE sizes.  PyTorch is used only to own device memory (tensor.data_ptr())."""
+import multiprocessing as mp
+
+import numpy as np
+import pytest
+
+from util import bits_equal, gold, product_config, sha
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(case):
+    config = product_config(case)
+    from lib import _native as nat
+    nat.configure_from(config)
+    nat.lib().bf_set_kernel_options(0, 1)
+    return config, nat, nat.lib()
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def test_batched_and_sharded_maps_equal_single_calls():
+    config, nat, L = _setup("c1")
+    torch = _torch()
+    from lib import directions
+    g = gold("c1")
+    mics = nat.i32(g["mic_ids"])
+    D, n, N, M = 400, 64, 256, 64
+    whole, d32 = directions.whole_and_f32()
+    L.load_coefficients_pad(nat.ptr(whole), whole.size)
+    L.load_coefficients_lerp(nat.ptr(d32), d32.size)
+    nat.check()
+    F = 5
+    rng = np.random.default_rng(11)
+    frames = rng.standard_normal((F, M, N)).astype(np.float32)
+    frames[0] = g["signals"]
+    d_sig = torch.from_numpy(frames).cuda()
+    d_mics = torch.from_numpy(mics).cuda()
+    for algo, name, key in ((nat.ALGO_PAD, "mimo_pad", "img_pad"), (nat.ALGO_LERP, "mimo_lerp", "img_lerp")):
+        single = np.zeros((F, D), np.float32)
+        for f in range(F):
+            getattr(L, name)(nat.ptr(frames[f]), nat.ptr(single[f]), nat.ptr(mics), n)
+            nat.check()
+        assert bits_equal(single[0], g[key])
+        d_img = torch.full((F, D), float("nan"), device="cuda")
+        nat.check(L.bf_mimo_dev(algo, d_sig.data_ptr(), d_img.data_ptr(), F, d_mics.data_ptr(), n, 0, D, None))
+        torch.cuda.synchronize()
+        assert bits_equal(d_img.cpu().numpy(), single)
+        # direction sharding: 3 uneven slices written into one image buffer
+        d_img2 = torch.full((F, D), float("nan"), device="cuda")
+        for lo, cnt in ((0, 133), (133, 134), (267, 133)):
+            nat.check(L.bf_mimo_dev(algo, d_sig.data_ptr(), d_img2.data_ptr(), F, d_mics.data_ptr(), n, lo, cnt, None))
+        torch.cuda.synchronize()
+        assert bits_equal(d_img2.cpu().numpy(), single)
+
+
+@pytest.mark.parametrize("algo_name", ["pad", "lerp"])
+@pytest.mark.parametrize("n_use,blocks", [(64, 300), (200, 37), (5, 8)])
+def test_miso_stream_vs_oracle(algo_name, n_use, blocks):
+    from oracle import cpu
+    torch = _torch()
+    from lib import _native as nat
+    L = nat.lib()
+    M, N, X, Y = 256, 256, 6, 5
+    nat.configure(M, N, 8, X, Y, 128.0)
+    rng = np.random.default_rng(blocks + n_use)
+    sig = rng.standard_normal((blocks, M, N)).astype(np.float32)
+    mics = nat.i32(np.sort(rng.permutation(M)[:n_use]))
+    whole = rng.integers(0, 60, (X * Y, n_use)).astype(np.int32)
+    d32 = (rng.random((X * Y, n_use)) * 59.5).astype(np.float32)
+    L.load_coefficients_pad(nat.ptr(whole), whole.size)
+    L.load_coefficients_lerp(nat.ptr(d32), d32.size)
+    nat.check()
+    off = 17 * n_use
+    algo = nat.ALGO_PAD if algo_name == "pad" else nat.ALGO_LERP
+    d_sig, d_mics = torch.from_numpy(sig).cuda(), torch.from_numpy(mics).cuda()
+    for scale in (0, 1):
+        d_out = torch.full((blocks, N), float("nan"), device="cuda")
+        nat.check(L.bf_miso_dev(algo, d_sig.data_ptr(), d_out.data_ptr(), blocks, d_mics.data_ptr(), n_use, off, scale, None))
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy()
+        for b in (0, 1, blocks // 2, blocks - 1):
+            ref = cpu.miso_pad(sig[b], mics, whole, off) if algo_name == "pad" else cpu.miso_lerp(sig[b], mics, d32, off)
+            if scale:
+                ref = cpu.miso_scale(ref, n_use, 128.0)
+            assert bits_equal(got[b], ref), (b, scale)
+    # the simple kernel gives the same stream
+    L.bf_set_kernel_options(1, 1)
+    d_out2 = torch.zeros((blocks, N), device="cuda")
+    nat.check(L.bf_miso_dev(algo, d_sig.data_ptr(), d_out2.data_ptr(), blocks, d_mics.data_ptr(), n_use, off, 1, None))
+    torch.cuda.synchronize()
+    L.bf_set_kernel_options(0, 1)
+    assert bits_equal(d_out2.cpu().numpy(), got)
+
+
+def test_full_size_c3_properties():
+    """BASELINE config C3 (256 mics, 180x180 grid) at full size: golden image from the reference,
+    tiled == simple on a slice, permutation/idempotence/scaling properties."""
+    config, nat, L = _setup("c3")
+    torch = _torch()
+    from lib import directions
+    g = gold("c3")
+    sig, mics = np.ascontiguousarray(g["signals"]), nat.i32(g["mic_ids"])
+    D, n = 32400, 256
+    directions.load_pad_from_geometry()                # generator -> device table, no host trip
+    img = np.zeros(D, np.float32)
+    L.mimo_pad(nat.ptr(sig), nat.ptr(img), nat.ptr(mics), n)
+    nat.check()
+    assert bits_equal(img, g["img_pad"])
+    img_again = np.zeros(D, np.float32)
+    L.mimo_pad(nat.ptr(sig), nat.ptr(img_again), nat.ptr(mics), n)
+    assert bits_equal(img, img_again)                   # idempotent / deterministic
+    # the strongest source (2 kHz, A = 0.1) dominates: global maximum on its grid column +-3
+    ix = int(np.argmax(img)) // 180
+    assert abs(ix - 40) <= 3, ix
+    # exact power-of-two scaling: signals*2 -> image*4, bit for bit
+    img4 = np.zeros(D, np.float32)
+    sig2 = (sig * np.float32(2)).astype(np.float32)
+    L.mimo_pad(nat.ptr(sig2), nat.ptr(img4), nat.ptr(mics), n)
+    assert bits_equal(img4, img * np.float32(4))
+    # lerp at full size
+    directions.load_lerp_from_geometry()
+    imgl = np.zeros(D, np.float32)
+    L.mimo_lerp(nat.ptr(sig), nat.ptr(imgl), nat.ptr(mics), n)
+    nat.check()
+    assert bits_equal(imgl, g["img_lerp"])
+    # tiled == simple on a 2000-direction slice (device API)
+    d_sig, d_mics = torch.from_numpy(sig[None]).cuda(), torch.from_numpy(mics).cuda()
+    outs = []
+    for simple in (0, 1):
+        L.bf_set_kernel_options(simple, 1)
+        d_img = torch.zeros((1, D), device="cuda")
+        nat.check(L.bf_mimo_dev(nat.ALGO_LERP, d_sig.data_ptr(), d_img.data_ptr(), 1, d_mics.data_ptr(), n, 15000, 2003, None))
+        torch.cuda.synchronize()
+        outs.append(d_img.cpu().numpy()[0, 15000:17003])
+    L.bf_set_kernel_options(0, 1)
+    assert bits_equal(outs[0], outs[1]) and bits_equal(outs[0], g["img_lerp"][15000:17003])
+    for i, d in enumerate(g["miso_dirs"]):
+        out = np.zeros(256, np.float32)
+        L.miso_lerp(nat.ptr(sig), nat.ptr(out), nat.ptr(mics), n, int(d) * n)
+        assert bits_equal(out, g["miso_lerp"][i])
+
+
+def _producer(target_name, q, running, case):
+    import os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "zybo-rt-sampler-image-detection_b200"))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    from util import gold, product_config
+    product_config(case)
+    from lib import beamformer
+    g = gold(case)
+    rec = np.concatenate([g["signals"], g["signals"][:, ::-1]], axis=1)
+    beamformer.connect(False, verbose=False, source=beamformer.ArraySource(rec))
+    getattr(beamformer, target_name)(q, running)
+
+
+@pytest.mark.parametrize("target", ["b", "uti_api"])
+def test_producer_loop_in_child_process(target):
+    """The reference runs its loops in multiprocessing.Process children created by fork
+    (main.pyx:702-721); CUDA must initialise lazily inside the child.  Payload contract: `b` puts
+    (power_map, frame_nr), the api loops put the bare map (camera.py:83, visual.py:421)."""
+    g = gold("c1")
+    ctx = mp.get_context("fork")
+    q, running = ctx.JoinableQueue(maxsize=4), ctx.Value("i", 1)
+    p = ctx.Process(target=_producer, args=(target, q, running, "c1"))
+    p.start()
+    try:
+        items = [q.get(timeout=120) for _ in range(3)]
+    finally:
+        running.value = 0
+        while True:
+            try:
+                q.get(timeout=2)
+            except Exception:  # noqa: BLE001
+                break
+        p.join(timeout=30)
+        if p.is_alive():
+            p.terminate()
+    first = items[0]
+    if target == "b":
+        assert isinstance(first, tuple) and first[1] == 1 and items[2][1] == 3
+        first = first[0]
+    assert first.shape == (20, 20) and first.dtype == np.float32 and first.flags["C_CONTIGUOUS"]
+    assert bits_equal(first.ravel(), g["img_pad"])
+
+
+def test_miso_beam_listen_and_steering():
+    config, nat, L = _setup("c1")
+    from oracle import cpu
+    from lib import beamformer, directions
+    g = gold("c1")
+    beamformer.connect(False, verbose=False, source=beamformer.ArraySource(g["signals"]))
+    try:
+        whole, _ = directions.whole_and_f32()
+        L.load_coefficients_pad(nat.ptr(whole), whole.size)
+        mics, n = directions.active_microphones()
+        beamformer.load_pa(mics, n)
+        off = beamformer.stear_miso_beam(14 / 20 + 0.01, 6 / 20 + 0.01)
+        assert off == int(6 * 20 * 64 + 14 * 64)
+        audio = beamformer.miso_listen(scaled=True)
+        ref = cpu.miso_scale(cpu.miso_pad(g["signals"], mics, whole, off), n, 128.0)
+        assert bits_equal(audio, ref)
+    finally:
+        beamformer.disconnect()

@@ -1,0 +1,682 @@
+// bf_api.cu -- process state and the C ABI of libbf_b200.so (include/bf_b200.h).
+//
+// Part-1 entry points keep the reference's names, signatures and ownership rules
+// (caller owns every pointer; load_* copies the table; one table per algorithm
+// per process).  They take HOST pointers: stage through
+// pinned memory, run on the current device, copy back, return.  CUDA is initialised
+// lazily on first use so that the library can be loaded before fork() the way the
+// reference's producer processes do (main.pyx:702-721).
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "bf_common.cuh"
+
+namespace bf {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_status = BF_OK;
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(int status, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    g_status = status;
+    if (getenv("BF_VERBOSE")) fprintf(stderr, "[bf_b200] error %d: %s\n", status, g_err);
+}
+void clear_error() { g_err[0] = 0; g_status = BF_OK; }
+int last_status() { return g_status; }
+void count_launch(int n) { g_launches += (uint64_t)n; }
+
+int DevBuf::ensure(size_t need)
+{
+    if (need <= bytes && p) return BF_OK;
+    if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+    size_t want = need < 256 ? 256 : need;
+    BF_CUDA(cudaMalloc(&p, want));
+    bytes = want;
+    return BF_OK;
+}
+void DevBuf::release()
+{
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+}
+
+State &state()
+{
+    static State S = [] {
+        State s;
+        // stock PC/src/config.json values
+        s.cfg.n_microphones = 256; s.cfg.n_samples = 256; s.cfg.n_taps = 8;
+        s.cfg.max_res_x = 57; s.cfg.max_res_y = 32; s.cfg.mic_gain = 128.0f; s.cfg.fir_fused = -1;
+        return s;
+    }();
+    return S;
+}
+
+int ensure_device()
+{
+    State &S = state();
+    if (S.sm_count > 0) return BF_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error(BF_ERR_CUDA, "no CUDA device available (%s): this library has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return BF_ERR_CUDA;
+    }
+    int dev = 0;
+    if (S.device >= 0) { BF_CUDA(cudaSetDevice(S.device)); dev = S.device; }
+    else BF_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    BF_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) {
+        set_error(BF_ERR_CUDA, "device %d is sm_%d%d; this build targets sm_100a only", dev,
+                  prop.major, prop.minor);
+        return BF_ERR_CUDA;
+    }
+    S.device = dev;
+    S.sm_count = prop.multiProcessorCount;
+    return BF_OK;
+}
+
+int ensure_pinned(size_t bytes)
+{
+    State &S = state();
+    if (bytes <= S.h_pinned_bytes) return BF_OK;
+    if (S.h_pinned) cudaFreeHost(S.h_pinned);
+    S.h_pinned = nullptr; S.h_pinned_bytes = 0;
+    BF_CUDA(cudaMallocHost(&S.h_pinned, bytes));
+    S.h_pinned_bytes = bytes;
+    return BF_OK;
+}
+
+static std::mutex g_mu;   // part-1 calls share global tables/staging, like the reference
+
+// ---- table installation --------------------------------------------------------
+static int install_pad(DevBuf &buf, size_t &count, int &wmax, GroupTable *gt, const int *src,
+                       size_t n, bool src_on_device)
+{
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (n == 0) { count = 0; return BF_OK; }
+    rc = buf.ensure(n * sizeof(int));
+    if (rc) return rc;
+    BF_CUDA(cudaMemcpy(buf.p, src, n * sizeof(int),
+                       src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    count = n;
+    rc = launch_max_abs_i32(buf.as<int>(), n, &wmax);
+    if (rc) return rc;
+    if (gt) gt->n = -1;            // invalidate the cached group layout
+    state().tab.version++;
+    return BF_OK;
+}
+
+static int install_lerp(const float *src, size_t n, bool src_on_device)
+{
+    State &S = state();
+    int rc = ensure_device();
+    if (rc) return rc;
+    Tables &T = S.tab;
+    if (n == 0) { T.lerp_count = 0; return BF_OK; }
+    if ((rc = T.lerp_whole.ensure(n * sizeof(int)))) return rc;
+    if ((rc = T.lerp_weight.ensure(n * sizeof(float)))) return rc;
+    const float *d_src = src;
+    if (!src_on_device) {
+        if ((rc = S.d_scratch.ensure(n * sizeof(float) + 256))) return rc;
+        BF_CUDA(cudaMemcpy(S.d_scratch.p, src, n * sizeof(float), cudaMemcpyHostToDevice));
+        d_src = S.d_scratch.as<float>();
+    }
+    if ((rc = split_lerp_dev(d_src, n, T.lerp_whole.as<int>(), T.lerp_weight.as<float>(), 0))) return rc;
+    BF_CUDA(cudaDeviceSynchronize());
+    T.lerp_count = n;
+    if ((rc = launch_max_abs_i32(T.lerp_whole.as<int>(), n, &T.lerp_max))) return rc;
+    T.g_lerp.n = -1;
+    T.version++;
+    return BF_OK;
+}
+
+static int install_fir(const float *src, size_t n, bool src_on_device)
+{
+    State &S = state();
+    int rc = ensure_device();
+    if (rc) return rc;
+    Tables &T = S.tab;
+    if (n == 0) { T.fir_count = 0; return BF_OK; }
+    if ((rc = T.fir_taps.ensure(n * sizeof(float)))) return rc;
+    BF_CUDA(cudaMemcpy(T.fir_taps.p, src, n * sizeof(float),
+                       src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    T.fir_count = n;
+    T.version++;
+    return BF_OK;
+}
+
+static int install_hybrid(const float *src, size_t n, bool src_on_device)
+{
+    State &S = state();
+    int rc = ensure_device();
+    if (rc) return rc;
+    Tables &T = S.tab;
+    const int taps = S.cfg.n_taps;
+    if (n == 0) { T.hyb_count = 0; return BF_OK; }
+    std::vector<float> h_d;
+    const float *h_src = src;
+    if (src_on_device) {
+        h_d.resize(n);
+        BF_CUDA(cudaMemcpy(h_d.data(), src, n * sizeof(float), cudaMemcpyDeviceToHost));
+        h_src = h_d.data();
+    }
+    std::vector<int> whole(n);
+    std::vector<float> tp(n * (size_t)taps);
+    split_hybrid_host(h_src, n, whole.data(), tp.data(), taps);
+    if ((rc = T.hyb_whole.ensure(n * sizeof(int)))) return rc;
+    if ((rc = T.hyb_taps.ensure(tp.size() * sizeof(float)))) return rc;
+    BF_CUDA(cudaMemcpy(T.hyb_whole.p, whole.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    BF_CUDA(cudaMemcpy(T.hyb_taps.p, tp.data(), tp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    T.hyb_count = n;
+    T.version++;
+    return BF_OK;
+}
+
+// ---- host-pointer MIMO / MISO ----------------------------------------------------
+static int mimo_dispatch(int algo, const float *d_sig, float *d_img, int frames, const int *d_mics,
+                         int n, int d_begin, int d_count, ImgLayout lay, cudaStream_t st)
+{
+    State &S = state();
+    const int N = S.cfg.n_samples;
+    if (lay.frame_stride == 0 && lay.dir_stride == 0)
+        lay = ImgLayout{(long)S.cfg.max_res_x * S.cfg.max_res_y, 1, 0};
+    const bool tiled_ok = (algo == BF_ALGO_PAD || algo == BF_ALGO_LERP || algo == -1) &&
+                          !S.simple_kernel && (N == 64 || N == 128 || N == 256);
+    if (tiled_ok) return mimo_tiled(algo, d_sig, d_img, frames, d_mics, n, d_begin, d_count, lay, st);
+    return mimo_simple(algo, d_sig, d_img, frames, d_mics, n, d_begin, d_count, lay, st);
+}
+
+static int check_n(int n, const char *who)
+{
+    State &S = state();
+    if (n <= 0 || n > S.cfg.n_microphones) {
+        set_error(BF_ERR_ARG, "%s: n = %d outside (0, N_MICROPHONES = %d]", who, n, S.cfg.n_microphones);
+        return BF_ERR_ARG;
+    }
+    return BF_OK;
+}
+
+static int upload_mics(const int *adaptive_array, int n)
+{
+    State &S = state();
+    for (int m = 0; m < n; m++)
+        if (adaptive_array[m] < 0 || adaptive_array[m] >= S.cfg.n_microphones) {
+            set_error(BF_ERR_ARG, "adaptive_array[%d] = %d outside [0, N_MICROPHONES)", m, adaptive_array[m]);
+            return BF_ERR_ARG;
+        }
+    int rc = S.d_mic_ids.ensure((size_t)n * sizeof(int));
+    if (rc) return rc;
+    BF_CUDA(cudaMemcpyAsync(S.d_mic_ids.p, adaptive_array, (size_t)n * sizeof(int),
+                            cudaMemcpyHostToDevice, 0));
+    return BF_OK;
+}
+
+static int host_mimo(int algo, const float *signals, float *image, const int *adaptive_array, int n)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    State &S = state();
+    int rc = ensure_device();
+    if (rc) return rc;
+    if ((rc = check_n(n, "mimo"))) return rc;
+    const size_t sig_b = (size_t)S.cfg.n_microphones * S.cfg.n_samples * sizeof(float);
+    const int D = S.cfg.max_res_x * S.cfg.max_res_y;
+    const size_t img_b = (size_t)D * sizeof(float);
+    if ((rc = ensure_pinned(sig_b + img_b))) return rc;
+    if ((rc = S.d_signals.ensure(sig_b))) return rc;
+    if ((rc = S.d_image.ensure(img_b))) return rc;
+    if ((rc = upload_mics(adaptive_array, n))) return rc;
+    // pageable -> pinned -> device keeps the H2D copy asynchronous and at full PCIe rate
+    memcpy(S.h_pinned, signals, sig_b);
+    BF_CUDA(cudaMemcpyAsync(S.d_signals.p, S.h_pinned, sig_b, cudaMemcpyHostToDevice, 0));
+    if ((rc = mimo_dispatch(algo, S.d_signals.as<float>(), S.d_image.as<float>(), 1,
+                            S.d_mic_ids.as<int>(), n, 0, D, ImgLayout{0, 0, 0}, 0)))
+        return rc;
+    float *h_img = (float *)((char *)S.h_pinned + sig_b);
+    BF_CUDA(cudaMemcpyAsync(h_img, S.d_image.p, img_b, cudaMemcpyDeviceToHost, 0));
+    BF_CUDA(cudaStreamSynchronize(0));
+    memcpy(image, h_img, img_b);
+    return BF_OK;
+}
+
+static int host_miso(int algo, const float *signals, float *out, const int *adaptive_array, int n,
+                     int offset, int by_mic)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    State &S = state();
+    int rc = ensure_device();
+    if (rc) return rc;
+    if ((rc = check_n(n, "miso"))) return rc;
+    const size_t sig_b = (size_t)S.cfg.n_microphones * S.cfg.n_samples * sizeof(float);
+    const size_t out_b = (size_t)S.cfg.n_samples * sizeof(float);
+    if ((rc = ensure_pinned(sig_b + out_b))) return rc;
+    if ((rc = S.d_signals.ensure(sig_b))) return rc;
+    if ((rc = S.d_out.ensure(out_b))) return rc;
+    if ((rc = upload_mics(adaptive_array, n))) return rc;
+    memcpy(S.h_pinned, signals, sig_b);
+    BF_CUDA(cudaMemcpyAsync(S.d_signals.p, S.h_pinned, sig_b, cudaMemcpyHostToDevice, 0));
+    if ((rc = miso_run(algo, S.d_signals.as<float>(), S.d_out.as<float>(), 1, S.d_mic_ids.as<int>(), n,
+                       offset, by_mic, 0, 0)))
+        return rc;
+    float *h_out = (float *)((char *)S.h_pinned + sig_b);
+    BF_CUDA(cudaMemcpyAsync(h_out, S.d_out.p, out_b, cudaMemcpyDeviceToHost, 0));
+    BF_CUDA(cudaStreamSynchronize(0));
+    memcpy(out, h_out, out_b);
+    return BF_OK;
+}
+
+static int sourced(float **sig_out)
+{
+    State &S = state();
+    if (!S.source) {
+        set_error(BF_ERR_ARG, "no data source registered: call bf_set_data_source() (get_data() "
+                              "of the reference's receiver stays host C, api.c:830-859)");
+        return BF_ERR_ARG;
+    }
+    static std::vector<float> buf;
+    buf.resize((size_t)S.cfg.n_microphones * S.cfg.n_samples);
+    S.source(buf.data());
+    *sig_out = buf.data();
+    return BF_OK;
+}
+
+}  // namespace bf
+
+using namespace bf;
+
+extern "C" {
+
+// =========================== part 2: configuration ==============================
+int bf_configure(const bf_config *cfg)
+{
+    clear_error();
+    if (!cfg) { set_error(BF_ERR_ARG, "bf_configure(NULL)"); return BF_ERR_ARG; }
+    if (cfg->n_microphones < 1 || cfg->n_samples < 1 || cfg->n_samples > 1024 || cfg->n_taps < 1 ||
+        cfg->max_res_x < 1 || cfg->max_res_y < 1) {
+        set_error(BF_ERR_CONFIG, "bad sizes: mics %d samples %d (1..1024) taps %d grid %dx%d",
+                  cfg->n_microphones, cfg->n_samples, cfg->n_taps, cfg->max_res_x, cfg->max_res_y);
+        return BF_ERR_CONFIG;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    State &S = state();
+    S.cfg = *cfg;
+    S.tab.g_pad.n = S.tab.g_lerp.n = S.tab.g_trunc.n = -1;
+    return BF_OK;
+}
+int bf_get_config(bf_config *cfg)
+{
+    if (!cfg) return BF_ERR_ARG;
+    *cfg = state().cfg;
+    return BF_OK;
+}
+const char *bf_last_error(void) { return g_err; }
+int bf_last_status(void) { return g_status; }
+int bf_device_count(void)
+{
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+    return c;
+}
+int bf_set_device(int ordinal)
+{
+    clear_error();
+    State &S = state();
+    if (S.sm_count > 0 && S.device != ordinal) {
+        set_error(BF_ERR_CONFIG, "device already initialised as %d; one device per process", S.device);
+        return BF_ERR_CONFIG;
+    }
+    S.device = ordinal;
+    return ensure_device();
+}
+const char *bf_version(void) { return "bf_b200 0.1 (sm_100a)"; }
+void bf_set_data_source(bf_data_source_fn fn) { state().source = fn; }
+int bf_set_kernel_options(int simple_kernel, int exact_sum)
+{
+    State &S = state();
+    if (simple_kernel >= 0) S.simple_kernel = simple_kernel;
+    if (exact_sum >= 0) S.exact_sum = exact_sum;
+    return BF_OK;
+}
+uint64_t bf_kernel_launches(int reset)
+{
+    uint64_t v = g_launches.load();
+    if (reset) g_launches = 0;
+    return v;
+}
+
+// =========================== part 2: device entry points ========================
+int bf_mimo_dev(int algo, const float *d_signals, float *d_images, int frames, const int *d_mic_ids,
+                int n, int d_begin, int d_count, void *stream)
+{
+    return bf_mimo_dev_ex(algo, d_signals, d_images, frames, d_mic_ids, n, d_begin, d_count, 0, 0, 0,
+                          stream);
+}
+
+int bf_mimo_dev_ex(int algo, const float *d_signals, float *d_images, int frames,
+                   const int *d_mic_ids, int n, int d_begin, int d_count, long frame_stride,
+                   long dir_stride, int d_origin, void *stream)
+{
+    clear_error();
+    State &S = state();
+    int rc = ensure_device();
+    if (rc) return rc;
+    if ((rc = check_n(n, "bf_mimo_dev"))) return rc;
+    const int D = S.cfg.max_res_x * S.cfg.max_res_y;
+    if (frames < 1 || d_begin < 0 || d_count < 1 || d_begin + d_count > D || !d_signals || !d_images || !d_mic_ids) {
+        set_error(BF_ERR_ARG, "bf_mimo_dev: frames %d slice [%d,+%d) of D=%d", frames, d_begin, d_count, D);
+        return BF_ERR_ARG;
+    }
+    return mimo_dispatch(algo, d_signals, d_images, frames, d_mic_ids, n, d_begin, d_count,
+                         ImgLayout{frame_stride, dir_stride, d_origin}, (cudaStream_t)stream);
+}
+
+int bf_miso_dev(int algo, const float *d_signals, float *d_out, int blocks, const int *d_mic_ids,
+                int n, int offset, int scale, void *stream)
+{
+    clear_error();
+    int rc = ensure_device();
+    if (rc) return rc;
+    if ((rc = check_n(n, "bf_miso_dev"))) return rc;
+    if (blocks < 1 || offset < 0 || !d_signals || !d_out || !d_mic_ids) {
+        set_error(BF_ERR_ARG, "bf_miso_dev: blocks %d offset %d", blocks, offset);
+        return BF_ERR_ARG;
+    }
+    return miso_run(algo, d_signals, d_out, blocks, d_mic_ids, n, offset, 0, scale, (cudaStream_t)stream);
+}
+
+int bf_load_table_dev(int algo, const void *d_table, size_t count)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    Tables &T = state().tab;
+    switch (algo) {
+        case BF_ALGO_PAD: return install_pad(T.pad_whole, T.pad_count, T.pad_max, &T.g_pad, (const int *)d_table, count, true);
+        case BF_ALGO_LERP: return install_lerp((const float *)d_table, count, true);
+        case BF_ALGO_FIR_SEQ: case BF_ALGO_FIR_LANES: return install_fir((const float *)d_table, count, true);
+        case BF_ALGO_HYBRID: return install_hybrid((const float *)d_table, count, true);
+    }
+    set_error(BF_ERR_ARG, "bf_load_table_dev: bad algo %d", algo);
+    return BF_ERR_ARG;
+}
+
+int bf_generate_delays(double k, const double *x_scan, int res_x, const double *y_scan, int res_y,
+                       double z2, const double *mic_x, const double *mic_y, int n,
+                       double *delays_f64, int *whole_i32, float *delays_f32, int load_algo)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    State &S = state();
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (res_x < 1 || res_y < 1 || n < 1 || !x_scan || !y_scan || !mic_x || !mic_y) {
+        set_error(BF_ERR_ARG, "bf_generate_delays: bad arguments");
+        return BF_ERR_ARG;
+    }
+    const size_t cnt = (size_t)res_x * res_y * n;
+    DevBuf d_in, d_f64, d_i32, d_f32;
+    const size_t in_cnt = (size_t)res_x + res_y + 2 * (size_t)n;
+    if ((rc = d_in.ensure(in_cnt * sizeof(double)))) return rc;
+    double *d_xs = d_in.as<double>(), *d_ys = d_xs + res_x, *d_mx = d_ys + res_y, *d_my = d_mx + n;
+    auto fail = [&](int r) { d_in.release(); d_f64.release(); d_i32.release(); d_f32.release(); return r; };
+#define BF_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_error(BF_ERR_CUDA, "%s -> %s", #x, cudaGetErrorString(_e)); return fail(BF_ERR_CUDA); } } while (0)
+    BF_TRY(cudaMemcpy(d_xs, x_scan, res_x * sizeof(double), cudaMemcpyHostToDevice));
+    BF_TRY(cudaMemcpy(d_ys, y_scan, res_y * sizeof(double), cudaMemcpyHostToDevice));
+    BF_TRY(cudaMemcpy(d_mx, mic_x, n * sizeof(double), cudaMemcpyHostToDevice));
+    BF_TRY(cudaMemcpy(d_my, mic_y, n * sizeof(double), cudaMemcpyHostToDevice));
+    const bool want_i32 = whole_i32 || load_algo == BF_ALGO_PAD;
+    const bool want_f32 = delays_f32 || load_algo == BF_ALGO_LERP || load_algo == BF_ALGO_HYBRID;
+    if (delays_f64 && (rc = d_f64.ensure(cnt * sizeof(double)))) return fail(rc);
+    if (want_i32 && (rc = d_i32.ensure(cnt * sizeof(int)))) return fail(rc);
+    if (want_f32 && (rc = d_f32.ensure(cnt * sizeof(float)))) return fail(rc);
+    if ((rc = delay_table_dev(k, d_xs, res_x, d_ys, res_y, z2, d_mx, d_my, n, d_f64.as<double>(),
+                              d_i32.as<int>(), d_f32.as<float>(), 0)))
+        return fail(rc);
+    BF_TRY(cudaDeviceSynchronize());
+    if (delays_f64) BF_TRY(cudaMemcpy(delays_f64, d_f64.p, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+    if (whole_i32) BF_TRY(cudaMemcpy(whole_i32, d_i32.p, cnt * sizeof(int), cudaMemcpyDeviceToHost));
+    if (delays_f32) BF_TRY(cudaMemcpy(delays_f32, d_f32.p, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+#undef BF_TRY
+    Tables &T = S.tab;
+    if (load_algo == BF_ALGO_PAD)
+        rc = install_pad(T.pad_whole, T.pad_count, T.pad_max, &T.g_pad, d_i32.as<int>(), cnt, true);
+    else if (load_algo == BF_ALGO_LERP)
+        rc = install_lerp(d_f32.as<float>(), cnt, true);
+    else if (load_algo == BF_ALGO_HYBRID)
+        rc = install_hybrid(d_f32.as<float>(), cnt, true);
+    else if (load_algo >= 0) { set_error(BF_ERR_ARG, "bf_generate_delays: load_algo %d", load_algo); rc = BF_ERR_ARG; }
+    return fail(rc);
+}
+
+int bf_get_lerp_tables(int *whole, float *weight, size_t count)
+{
+    clear_error();
+    Tables &T = state().tab;
+    if (count > T.lerp_count) { set_error(BF_ERR_NOT_LOADED, "lerp table holds %zu entries", T.lerp_count); return BF_ERR_NOT_LOADED; }
+    if (whole) BF_CUDA(cudaMemcpy(whole, T.lerp_whole.p, count * sizeof(int), cudaMemcpyDeviceToHost));
+    if (weight) BF_CUDA(cudaMemcpy(weight, T.lerp_weight.p, count * sizeof(float), cudaMemcpyDeviceToHost));
+    return BF_OK;
+}
+int bf_get_hybrid_tables(int *whole, float *taps, size_t count)
+{
+    clear_error();
+    State &S = state();
+    Tables &T = S.tab;
+    if (count > T.hyb_count) { set_error(BF_ERR_NOT_LOADED, "hybrid table holds %zu entries", T.hyb_count); return BF_ERR_NOT_LOADED; }
+    if (whole) BF_CUDA(cudaMemcpy(whole, T.hyb_whole.p, count * sizeof(int), cudaMemcpyDeviceToHost));
+    if (taps) BF_CUDA(cudaMemcpy(taps, T.hyb_taps.p, count * S.cfg.n_taps * sizeof(float), cudaMemcpyDeviceToHost));
+    return BF_OK;
+}
+
+// =========================== part 1: drop-in names ==============================
+// ---- pad_and_sum.h ----
+void load_coefficients_pad(int *whole_samples, int n)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    Tables &T = state().tab;
+    install_pad(T.pad_whole, T.pad_count, T.pad_max, &T.g_pad, whole_samples, n < 0 ? 0 : (size_t)n, false);
+}
+void load_coefficients_pad2(int *whole_miso, int n)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    Tables &T = state().tab;
+    int dummy;
+    install_pad(T.pad2_whole, T.pad2_count, dummy, nullptr, whole_miso, n < 0 ? 0 : (size_t)n, false);
+}
+void unload_coefficients_pad(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Tables &T = state().tab;
+    T.pad_whole.release(); T.pad_count = 0; T.g_pad.offs.release(); T.g_pad.n = -1;
+}
+void unload_coefficients_pad2(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Tables &T = state().tab;
+    T.pad2_whole.release(); T.pad2_count = 0;
+}
+void pad_delay(float *signal, float *out, int pos_pad)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    single_delay(0, signal, nullptr, 0.0f, pos_pad, out);
+}
+void miso_pad(float *signals, float *out, int *adaptive_array, int n, int offset)
+{
+    host_miso(BF_ALGO_PAD, signals, out, adaptive_array, n, offset, 0);
+}
+void miso_pad2(float *signals, float *out, int *adaptive_array, int n, int offset)
+{
+    (void)offset;   // unused by the reference too (pad_and_sum.c:77-92)
+    host_miso(BF_ALGO_PAD, signals, out, adaptive_array, n, 0, 1);
+}
+void mimo_pad(float *signals, float *image, int *adaptive_array, int n)
+{
+    host_mimo(BF_ALGO_PAD, signals, image, adaptive_array, n);
+}
+
+// ---- lerp_and_sum.h ----
+void load_coefficients_lerp(float *delays, int n)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    install_lerp(delays, n < 0 ? 0 : (size_t)n, false);
+}
+void unload_coefficients_lerp(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Tables &T = state().tab;
+    T.lerp_whole.release(); T.lerp_weight.release(); T.lerp_count = 0;
+    T.g_lerp.offs.release(); T.g_lerp.wts.release(); T.g_lerp.n = -1;
+}
+void lerp_delay(float *signal, float *out, float h, int pad)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    single_delay(1, signal, nullptr, h, pad, out);
+}
+void miso_lerp(float *signals, float *out, int *adaptive_array, int n, int offset)
+{
+    host_miso(BF_ALGO_LERP, signals, out, adaptive_array, n, offset, 0);
+}
+void mimo_lerp(float *signals, float *image, int *adaptive_array, int n)
+{
+    host_mimo(BF_ALGO_LERP, signals, image, adaptive_array, n);
+}
+
+// ---- convolve_and_sum.h ----
+void load_coefficients_convolve(float *h, int n)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    install_fir(h, n < 0 ? 0 : (size_t)n, false);
+}
+void unload_coefficients_convolve(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Tables &T = state().tab;
+    T.fir_taps.release(); T.fir_count = 0;
+}
+void convolve_delay_naive_add(float *signal, float *h, float *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    single_delay(2, signal, h, 0.0f, 0, out);
+}
+void convolve_delay_naive(float *signal, float *out, float *h)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    single_delay(2, signal, h, 0.0f, 0, out);
+}
+void convolve_delay_vectorized(float *signal, float *h, float *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    single_delay(4, signal, h, 0.0f, 0, out);
+}
+void convolve_delay_vectorized_add(float *signal, float *h, float *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    single_delay(3, signal, h, 0.0f, 0, out);
+}
+void miso_convolve_naive(float *signals, float *out, int *adaptive_array, int n, int offset)
+{
+    host_miso(BF_ALGO_FIR_SEQ, signals, out, adaptive_array, n, offset, 0);
+}
+void miso_convolve_vectorized(float *signals, float *out, int *adaptive_array, int n, int offset)
+{
+    host_miso(BF_ALGO_FIR_LANES, signals, out, adaptive_array, n, offset, 0);
+}
+void mimo_convolve_naive(float *signals, float *image, int *adaptive_array, int n)
+{
+    host_mimo(BF_ALGO_FIR_SEQ, signals, image, adaptive_array, n);
+}
+void mimo_convolve_vectorized(float *signals, float *image, int *adaptive_array, int n)
+{
+    host_mimo(BF_ALGO_FIR_LANES, signals, image, adaptive_array, n);
+}
+
+// ---- hybrid_convolve_and_sum.h ----
+void load_coefficients_convolve_hybrid(float *h, int n)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    install_hybrid(h, n < 0 ? 0 : (size_t)n, false);
+}
+void unload_coefficients_convolve_hybrid(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Tables &T = state().tab;
+    T.hyb_whole.release(); T.hyb_taps.release(); T.hyb_count = 0;
+}
+void convolve_hybrid_delay_add(float *signal, float *h, int pad, float *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    single_delay(5, signal, h, 0.0f, pad, out);
+}
+void miso_convolve_hybrid(float *signals, float *out, int *adaptive_array, int n, int offset)
+{
+    host_miso(BF_ALGO_HYBRID, signals, out, adaptive_array, n, offset, 0);
+}
+void mimo_convolve_hybrid(float *signals, float *image, int *adaptive_array, int n)
+{
+    host_mimo(BF_ALGO_HYBRID, signals, image, adaptive_array, n);
+}
+
+// ---- api.h wrappers: buffer from the registered source, then the kernel ----
+void pad_mimo(float *image, int *adaptive_array, int n)
+{
+    float *sig;
+    if (sourced(&sig) == BF_OK) host_mimo(BF_ALGO_PAD, sig, image, adaptive_array, n);
+}
+void lerp_mimo(float *image, int *adaptive_array, int n)
+{
+    float *sig;
+    if (sourced(&sig) == BF_OK) host_mimo(BF_ALGO_LERP, sig, image, adaptive_array, n);
+}
+void convolve_mimo_naive(float *image, int *adaptive_array, int n)
+{
+    float *sig;
+    if (sourced(&sig) == BF_OK) host_mimo(BF_ALGO_FIR_SEQ, sig, image, adaptive_array, n);
+}
+void convolve_mimo_vectorized(float *image, int *adaptive_array, int n)
+{
+    float *sig;
+    if (sourced(&sig) == BF_OK) host_mimo(BF_ALGO_FIR_LANES, sig, image, adaptive_array, n);
+}
+void load_coefficients2(int *whole_samples, int n)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    Tables &T = state().tab;
+    install_pad(T.trunc_whole, T.trunc_count, T.trunc_max, &T.g_trunc, whole_samples, n < 0 ? 0 : (size_t)n, false);
+}
+void mimo_truncated(float *image, int *adaptive_array, int n)
+{
+    float *sig;
+    if (sourced(&sig) == BF_OK) host_mimo(-1, sig, image, adaptive_array, n);
+}
+void miso_steer_listen(float *out, int *adaptive_array, int n, int steer_offset)
+{
+    float *sig;
+    if (sourced(&sig) == BF_OK) host_miso(BF_ALGO_PAD, sig, out, adaptive_array, n, steer_offset, 0);
+}
+
+}  // extern "C"

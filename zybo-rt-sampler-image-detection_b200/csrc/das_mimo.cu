@@ -1,0 +1,457 @@
+// das_mimo.cu -- time-domain delay-and-sum power maps (MIMO), tiled TMA kernel.
+//
+// Replaces mimo_pad (algorithms/pad_and_sum.c:100-143), mimo_lerp
+// (algorithms/lerp_and_sum.c:103-136) and the inline trunc-and-sum copy
+// (api.c:1014-1062) of the reference:
+//
+//   img[d] = 1/N * sum_t ( 1/n * sum_m  delayed_m,d[t] )^2
+//
+// Design (B200 / sm_100a):
+//   * persistent grid, one CTA per SM; a CTA = 1 producer warp + W consumer warps
+//   * a consumer warp owns a GROUP of R = 8 consecutive directions and all N
+//     samples of them in registers (lane l holds samples l, l+32, ...), so the
+//     microphone sum runs in the reference's order (m = 0..n-1, fp32) and the
+//     summed block out[t] is bit-identical to the CPU reference
+//   * microphone rows are streamed through a 4-stage shared-memory ring by the
+//     producer warp with 1-D bulk TMA copies (cp.async.bulk, SASS UBLKCP)
+//     completing on mbarriers; each row is stored behind a block of zeros so a
+//     delayed read is just an offset load (no predicates in the inner loop)
+//   * consecutive directions mostly share their integer delay for a microphone
+//     (the table varies slowly along the grid), so one shifted row load is
+//     reused for all directions of the group with the same delay: shared-memory
+//     traffic drops by ~R and the kernel becomes FP32-issue bound; the adds are
+//     issued as packed add.f32x2 / fma.f32x2 (FADD2/FFMA2)
+//   * the epilogue reproduces out/n, square, in-order sum over t, /N exactly
+//     (exact_sum) or uses a warp-shuffle tree
+//
+// Tables are re-laid out once per load into "group entries" (8 x u16 byte offsets
+// per (group, mic), + 8 fp32 weights for lerp) read with one uniform 16-byte load.
+#include "bf_common.cuh"
+
+namespace bf {
+
+static constexpr int kR = 8;           // directions per warp
+static constexpr int kStages = 4;      // smem ring depth
+static constexpr int kMaxWarps = 15;   // consumer warps per CTA (+1 producer = 512 threads, 128 regs)
+static constexpr int kScratchStride = 68;
+
+// ---------------------------------------------------------------------------
+// group-table builder
+// ---------------------------------------------------------------------------
+// One thread per (group, mic).  off = (P - w [- 1 for lerp]) * 4 bytes, so that
+// row_base + off + 4*t addresses sample (t - w [- 1]) of a row stored behind P
+// zeros.  Bit 0 of the first u16 flags "all 8 offsets equal".
+__global__ void build_groups_kernel(const int *__restrict__ whole, const float *__restrict__ weight,
+                                    uint4 *__restrict__ offs, float *__restrict__ wts, int n,
+                                    int d_begin, int d_count, int groups, int P, int w_hi,
+                                    int lerp)
+{
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= groups * n) return;
+    int g = idx / n, m = idx - g * n;
+    uint32_t o[kR];
+    bool same = true;
+#pragma unroll
+    for (int r = 0; r < kR; r++) {
+        int dl = g * kR + r;
+        if (dl >= d_count) dl = d_count - 1;            // tail group: replicate last direction
+        size_t e = (size_t)(d_begin + dl) * n + m;
+        int w = whole[e];
+        w = w < 0 ? 0 : (w > w_hi ? w_hi : w);
+        o[r] = (uint32_t)(P - w - (lerp ? 1 : 0)) * 4u;
+        if (o[r] != o[0]) same = false;
+        if (lerp) wts[(size_t)idx * kR + r] = weight[e];
+    }
+    uint4 v;
+    v.x = (o[0] | (same ? 1u : 0u)) | (o[1] << 16);
+    v.y = o[2] | (o[3] << 16);
+    v.z = o[4] | (o[5] << 16);
+    v.w = o[6] | (o[7] << 16);
+    offs[idx] = v;
+}
+
+static int build_groups(GroupTable &gt, const int *d_whole, const float *d_weight, int n,
+                        int d_begin, int d_count, int P, int n_samples, bool lerp,
+                        cudaStream_t st)
+{
+    int groups = (d_count + kR - 1) / kR;
+    size_t entries = (size_t)groups * n;
+    int rc = gt.offs.ensure(entries * sizeof(uint4));
+    if (rc) return rc;
+    if (lerp) {
+        rc = gt.wts.ensure(entries * kR * sizeof(float));
+        if (rc) return rc;
+    }
+    int w_hi = lerp ? n_samples - 1 : n_samples;
+    int threads = 256;
+    int blocks = (int)((entries + threads - 1) / threads);
+    build_groups_kernel<<<blocks, threads, 0, st>>>(d_whole, d_weight, gt.offs.as<uint4>(),
+                                                    gt.wts.as<float>(), n, d_begin, d_count,
+                                                    groups, P, w_hi, lerp ? 1 : 0);
+    BF_CHECK_LAUNCH();
+    count_launch();
+    gt.n = n; gt.d_begin = d_begin; gt.d_count = d_count; gt.pad = P; gt.n_samples = n_samples;
+    gt.groups = groups;
+    return BF_OK;
+}
+
+// lerp needs the per-row first difference s[i+1]-s[i] (lerp_and_sum.c:54); it is
+// computed once per frame in table-column order so that the main kernel can
+// bulk-copy it like a signal row.  diff[f][m][N-1] = 0 (never read).
+__global__ void diff_rows_kernel(const float *__restrict__ sig, const int *__restrict__ mic_ids,
+                                 float *__restrict__ diff, int n, int N, int n_mics_total)
+{
+    int f = blockIdx.y, m = blockIdx.x;
+    const float *row = sig + ((size_t)f * n_mics_total + mic_ids[m]) * N;
+    float *out = diff + ((size_t)f * n + m) * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+        out[i] = (i + 1 < N) ? __fsub_rn(row[i + 1], row[i]) : 0.0f;
+}
+
+// ---------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------
+struct MimoParams {
+    const float *sig;        // [frames][n_mics_total][N]
+    const float *diff;       // [frames][n][N] (lerp only)
+    float *img;              // [frames][D_total]
+    const int *mic_ids;      // [n]
+    const uint4 *offs;       // [groups][n]
+    const float *wts;        // [groups][n][8]
+    int n, n_mics_total, d_begin, d_count, frames;
+    long img_fs, img_ds;     // output strides (frame, direction)
+    int d_origin;
+    int groups;              // groups per frame
+    int tiles_per_frame, total_tiles;
+    int W;                   // consumer warps
+    int Mt;                  // mic rows per stage
+    int P;                   // zero floats in front of every row
+    int n_pow2;              // n is a power of two -> exact reciprocal multiply
+    float fn, inv_n;
+};
+
+template <int J>
+__device__ __forceinline__ void load_row(const char *p, float2 (&v)[J / 2])
+{
+#pragma unroll
+    for (int q = 0; q < J / 2; q++) {
+        v[q].x = *(const float *)(p + q * 256);
+        v[q].y = *(const float *)(p + q * 256 + 128);
+    }
+}
+
+template <int J, bool LERP, bool EXACT>
+__global__ void __launch_bounds__((kMaxWarps + 1) * 32, 1) das_mimo_kernel(const MimoParams p)
+{
+    constexpr int N = J * 32;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int W = p.W;
+    const int RS = p.P + N;                              // row stride in floats
+    const int arrays = LERP ? 2 : 1;
+    const size_t row_bytes = (size_t)RS * 4;
+    const size_t stage_bytes = (size_t)p.Mt * arrays * row_bytes;
+
+    uint64_t *full = (uint64_t *)smem;                   // [kStages]
+    uint64_t *empty = full + kStages;                    // [kStages]
+    unsigned char *stages = smem + 128;
+    float *scratch_all = (float *)(stages + kStages * stage_bytes);
+
+    // ---- prologue: zero the pad columns once, init barriers ----------------
+    {
+        const int rows_total = kStages * p.Mt * arrays;
+        for (int i = threadIdx.x; i < rows_total * p.P; i += blockDim.x) {
+            int row = i / p.P, c = i - row * p.P;
+            ((float *)(stages + (size_t)row * row_bytes))[c] = 0.0f;
+        }
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < kStages; s++) {
+                bfptx::mbar_init(&full[s], 1);
+                bfptx::mbar_init(&empty[s], W);
+            }
+            bfptx::fence_mbar_init();
+        }
+    }
+    __syncthreads();
+
+    const int nchunks = (p.n + p.Mt - 1) / p.Mt;
+
+    if (warp == W) {
+        // =================== producer warp ==================================
+        int s = 0;
+        uint32_t ph = 1;                                  // fresh barrier: parity-1 wait passes
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int frame = tile / p.tiles_per_frame;
+            const float *fsig = p.sig + (size_t)frame * p.n_mics_total * N;
+            const float *fdiff = LERP ? p.diff + (size_t)frame * p.n * N : nullptr;
+            for (int c = 0; c < nchunks; c++) {
+                const int m0 = c * p.Mt;
+                const int cnt = min(p.Mt, p.n - m0);
+                bfptx::mbar_wait(&empty[s], ph);
+                if (lane == 0)
+                    bfptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(cnt * arrays * N * 4));
+                __syncwarp();
+                unsigned char *sb = stages + (size_t)s * stage_bytes;
+                for (int r = lane; r < cnt; r += 32) {
+                    const int mic = p.mic_ids[m0 + r];
+                    float *dst = (float *)(sb + (size_t)r * arrays * row_bytes) + p.P;
+                    bfptx::bulk_g2s(dst, fsig + (size_t)mic * N, N * 4, &full[s]);
+                    if (LERP)
+                        bfptx::bulk_g2s(dst + RS, fdiff + (size_t)(m0 + r) * N, N * 4, &full[s]);
+                }
+                if (++s == kStages) { s = 0; ph ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ======================= consumer warps =================================
+    float *scratch = scratch_all + warp * (kR * kScratchStride);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int frame = tile / p.tiles_per_frame;
+        const int g = (tile - frame * p.tiles_per_frame) * W + warp;
+        const bool active = g < p.groups;
+        const uint4 *offs = p.offs + (size_t)(active ? g : 0) * p.n;
+        const float4 *wts = LERP ? (const float4 *)(p.wts + (size_t)(active ? g : 0) * p.n * kR)
+                                 : nullptr;
+
+        float2 acc[kR][J / 2];
+#pragma unroll
+        for (int r = 0; r < kR; r++)
+#pragma unroll
+            for (int q = 0; q < J / 2; q++) acc[r][q] = make_float2(0.f, 0.f);
+
+        for (int c = 0; c < nchunks; c++) {
+            const int m0 = c * p.Mt;
+            const int cnt = min(p.Mt, p.n - m0);
+            uint4 e_next = active ? __ldg(offs + m0) : make_uint4(0, 0, 0, 0);
+            bfptx::mbar_wait(&full[s], ph);
+            if (active) {
+                const char *rowp = (const char *)(stages + (size_t)s * stage_bytes) + lane * 4;
+                for (int mm = 0; mm < cnt; mm++, rowp += arrays * row_bytes) {
+                    const uint4 e = e_next;
+                    if (mm + 1 < cnt) e_next = __ldg(offs + m0 + mm + 1);
+                    float h[kR];
+                    if (LERP) {
+                        const float4 h0 = __ldg(wts + (size_t)(m0 + mm) * 2);
+                        const float4 h1 = __ldg(wts + (size_t)(m0 + mm) * 2 + 1);
+                        h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w;
+                        h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
+                    }
+                    if (e.x & 1u) {
+                        // ---- fast path: one shifted row serves all 8 directions
+                        const uint32_t o = e.x & 0xfffcu;
+                        float2 a[J / 2], b[J / 2];
+                        load_row<J>(rowp + o, a);
+                        if (LERP) load_row<J>(rowp + row_bytes + o, b);
+#pragma unroll
+                        for (int r = 0; r < kR; r++) {
+                            const float2 hh = make_float2(h[r], h[r]);
+#pragma unroll
+                            for (int q = 0; q < J / 2; q++) {
+                                if (LERP)
+                                    acc[r][q] = __fadd2_rn(acc[r][q], __ffma2_rn(hh, b[q], a[q]));
+                                else
+                                    acc[r][q] = __fadd2_rn(acc[r][q], a[q]);
+                            }
+                        }
+                    } else {
+                        // ---- general path: reload only when the delay changes
+                        const uint32_t ow[4] = {e.x & 0xfffcfffcu, e.y, e.z, e.w};
+                        uint32_t prev = 0xffffffffu;
+                        float2 a[J / 2], b[J / 2];
+#pragma unroll
+                        for (int r = 0; r < kR; r++) {
+                            const uint32_t o = (r & 1) ? (ow[r >> 1] >> 16) : (ow[r >> 1] & 0xffffu);
+                            if (o != prev) {
+                                load_row<J>(rowp + o, a);
+                                if (LERP) load_row<J>(rowp + row_bytes + o, b);
+                                prev = o;
+                            }
+                            const float2 hh = make_float2(h[r], h[r]);
+#pragma unroll
+                            for (int q = 0; q < J / 2; q++) {
+                                if (LERP)
+                                    acc[r][q] = __fadd2_rn(acc[r][q], __ffma2_rn(hh, b[q], a[q]));
+                                else
+                                    acc[r][q] = __fadd2_rn(acc[r][q], a[q]);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) bfptx::mbar_arrive(&empty[s]);
+            if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+
+        if (!active) continue;
+
+        // ---- epilogue: out/n, square, sum over t, /N (pad_and_sum.c:122-131) ----
+        float *img = p.img + (long)frame * p.img_fs + (long)(p.d_begin + g * kR - p.d_origin) * p.img_ds;
+        const int valid = min(kR, p.d_count - g * kR);
+        const long ds = p.img_ds;
+        if (EXACT) {
+            float run = 0.0f;
+#pragma unroll
+            for (int q = 0; q < J / 2; q++) {
+#pragma unroll
+                for (int r = 0; r < kR; r++) {
+                    float x0 = acc[r][q].x, x1 = acc[r][q].y;
+                    if (p.n_pow2) { x0 = __fmul_rn(x0, p.inv_n); x1 = __fmul_rn(x1, p.inv_n); }
+                    else          { x0 = __fdiv_rn(x0, p.fn);    x1 = __fdiv_rn(x1, p.fn); }
+                    scratch[r * kScratchStride + lane] = __fmul_rn(x0, x0);
+                    scratch[r * kScratchStride + 32 + lane] = __fmul_rn(x1, x1);
+                }
+                __syncwarp();
+                if (lane < kR) {
+                    const float4 *s4 = (const float4 *)(scratch + lane * kScratchStride);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float4 v = s4[i];
+                        run = __fadd_rn(run, v.x);
+                        run = __fadd_rn(run, v.y);
+                        run = __fadd_rn(run, v.z);
+                        run = __fadd_rn(run, v.w);
+                    }
+                }
+                __syncwarp();
+            }
+            if (lane < valid) img[lane * ds] = __fmul_rn(run, 1.0f / (float)N);
+        } else {
+            float tot[kR];
+#pragma unroll
+            for (int r = 0; r < kR; r++) {
+                float t = 0.0f;
+#pragma unroll
+                for (int q = 0; q < J / 2; q++) {
+                    float x0 = acc[r][q].x, x1 = acc[r][q].y;
+                    if (p.n_pow2) { x0 = __fmul_rn(x0, p.inv_n); x1 = __fmul_rn(x1, p.inv_n); }
+                    else          { x0 = __fdiv_rn(x0, p.fn);    x1 = __fdiv_rn(x1, p.fn); }
+                    t = fmaf(x0, x0, t);
+                    t = fmaf(x1, x1, t);
+                }
+#pragma unroll
+                for (int sh = 16; sh > 0; sh >>= 1) t += __shfl_xor_sync(0xffffffffu, t, sh);
+                tot[r] = t;
+            }
+            float mine = 0.0f;
+#pragma unroll
+            for (int r = 0; r < kR; r++)
+                if (lane == r) mine = tot[r];
+            if (lane < valid) img[lane * ds] = __fmul_rn(mine, 1.0f / (float)N);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host launcher
+// ---------------------------------------------------------------------------
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+template <int J>
+static int launch_J(bool lerp, bool exact, const MimoParams &mp, int grid, size_t smem,
+                    cudaStream_t st)
+{
+    auto go = [&](auto kern) -> int {
+        BF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, (mp.W + 1) * 32, smem, st>>>(mp);
+        BF_CHECK_LAUNCH();
+        count_launch();
+        return BF_OK;
+    };
+    if (lerp) return exact ? go(das_mimo_kernel<J, true, true>) : go(das_mimo_kernel<J, true, false>);
+    return exact ? go(das_mimo_kernel<J, false, true>) : go(das_mimo_kernel<J, false, false>);
+}
+
+int mimo_tiled(int algo, const float *d_sig, float *d_img, int frames, const int *d_mics, int n,
+               int d_begin, int d_count, ImgLayout lay, cudaStream_t st)
+{
+    State &S = state();
+    const int N = S.cfg.n_samples;
+    const int D = S.cfg.max_res_x * S.cfg.max_res_y;
+    const bool lerp = (algo == BF_ALGO_LERP);
+    if (N != 64 && N != 128 && N != 256) {
+        set_error(BF_ERR_CONFIG, "tiled kernel supports N_SAMPLES in {64,128,256}, got %d", N);
+        return BF_ERR_CONFIG;
+    }
+    Tables &T = S.tab;
+    const int *whole; const float *weight = nullptr; size_t count; int wmax; GroupTable *gt;
+    if (algo == BF_ALGO_PAD)       { whole = T.pad_whole.as<int>(); count = T.pad_count; wmax = T.pad_max; gt = &T.g_pad; }
+    else if (algo == BF_ALGO_LERP) { whole = T.lerp_whole.as<int>(); weight = T.lerp_weight.as<float>(); count = T.lerp_count; wmax = T.lerp_max; gt = &T.g_lerp; }
+    else if (algo == -1)           { whole = T.trunc_whole.as<int>(); count = T.trunc_count; wmax = T.trunc_max; gt = &T.g_trunc; }
+    else { set_error(BF_ERR_ARG, "mimo_tiled: bad algo %d", algo); return BF_ERR_ARG; }
+    if (count < (size_t)D * n || whole == nullptr) {
+        set_error(BF_ERR_NOT_LOADED, "coefficient table holds %zu entries, need D*n = %d*%d", count, D, n);
+        return BF_ERR_NOT_LOADED;
+    }
+    // zero-pad width of the smem rows: covers the largest (clamped) delay in the table
+    const int w_hi = lerp ? N - 1 : N;
+    int wc = wmax < 0 ? 0 : (wmax > w_hi ? w_hi : wmax);
+    const int P = round_up(wc + (lerp ? 1 : 0), 32);
+    if (gt->n != n || gt->d_begin != d_begin || gt->d_count != d_count || gt->pad != P ||
+        gt->n_samples != N) {
+        int rc = build_groups(*gt, whole, weight, n, d_begin, d_count, P, N, lerp, st);
+        if (rc) return rc;
+    }
+    const float *d_diff = nullptr;
+    if (lerp) {
+        int rc = S.d_diff.ensure((size_t)frames * n * N * sizeof(float));
+        if (rc) return rc;
+        diff_rows_kernel<<<dim3(n, frames), 128, 0, st>>>(d_sig, d_mics, S.d_diff.as<float>(), n, N,
+                                                          S.cfg.n_microphones);
+        BF_CHECK_LAUNCH();
+        count_launch();
+        d_diff = S.d_diff.as<float>();
+    }
+
+    MimoParams mp{};
+    mp.sig = d_sig; mp.diff = d_diff; mp.img = d_img; mp.mic_ids = d_mics;
+    mp.offs = gt->offs.as<uint4>(); mp.wts = gt->wts.as<float>();
+    mp.n = n; mp.n_mics_total = S.cfg.n_microphones;
+    mp.img_fs = lay.frame_stride; mp.img_ds = lay.dir_stride; mp.d_origin = lay.d_origin;
+    mp.d_begin = d_begin; mp.d_count = d_count; mp.frames = frames;
+    mp.groups = gt->groups;
+    mp.P = P;
+    mp.fn = (float)n; mp.inv_n = 1.0f / (float)n; mp.n_pow2 = (n & (n - 1)) == 0;
+
+    const long total_groups = (long)gt->groups * frames;
+    int W = (int)((total_groups + S.sm_count - 1) / S.sm_count);
+    W = W < 1 ? 1 : (W > kMaxWarps ? kMaxWarps : W);
+    if (W > 4) W = (round_up(W + 1, 4) - 1) > kMaxWarps ? kMaxWarps : (round_up(W + 1, 4) - 1);
+    mp.W = W;
+    mp.tiles_per_frame = (gt->groups + W - 1) / W;
+    mp.total_tiles = mp.tiles_per_frame * frames;
+    int grid = mp.total_tiles < S.sm_count ? mp.total_tiles : S.sm_count;
+
+    // stage geometry: as many mic rows per stage as fit in the smem budget
+    const size_t row_bytes = (size_t)(P + N) * 4 * (lerp ? 2 : 1);
+    const size_t scratch_bytes = (size_t)W * kR * kScratchStride * 4;
+    const size_t budget = 227 * 1024 - 128 - scratch_bytes - 1024;
+    int Mt = 32;
+    while (Mt > 1 && (size_t)Mt * row_bytes * kStages > budget) Mt >>= 1;
+    if ((size_t)Mt * row_bytes * kStages > budget) {
+        set_error(BF_ERR_CONFIG, "shared memory budget exceeded (row %zu bytes)", row_bytes);
+        return BF_ERR_CONFIG;
+    }
+    if (Mt > n) Mt = n;
+    mp.Mt = Mt;
+    const size_t smem = 128 + (size_t)kStages * Mt * row_bytes + scratch_bytes;
+
+    if (((uintptr_t)d_sig & 15) != 0) {
+        set_error(BF_ERR_ARG, "signal buffer must be 16-byte aligned for bulk copies");
+        return BF_ERR_ARG;
+    }
+    const bool exact = S.exact_sum != 0;
+    switch (N) {
+        case 64:  return launch_J<2>(lerp, exact, mp, grid, smem, st);
+        case 128: return launch_J<4>(lerp, exact, mp, grid, smem, st);
+        case 256: return launch_J<8>(lerp, exact, mp, grid, smem, st);
+    }
+    set_error(BF_ERR_CONFIG, "unsupported N_SAMPLES %d", N);
+    return BF_ERR_CONFIG;
+}
+
+}  // namespace bf

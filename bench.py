@@ -211,6 +211,52 @@ class ClockSampler:
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+
+def miso_c2(args, nat, L, config, directions, torch, stream, hbm_peak):
+    """BASELINE config C2: MISO single-beam output, 64-mic 8x8 array, a continuous stream of
+    256-sample blocks (2^16 blocks = 4.3 GB, HBM-resident, >> L2), pad and lerp delays, with the
+    audio loop's /n*MIC_GAIN post-scale.  Per block: 64 rows x 1 KiB read + table row + 1 KiB
+    written = 67 072 B for 16 384 MAC -> HBM-bound."""
+    wl = WORKLOADS["c1"]
+    config.reload(N_MICROPHONES=64, N_SAMPLES=256, MAX_RES_X=20, MAX_RES_Y=20, N_TAPS=8, SKIP_N_MICS=1,
+                  GEOMETRY_N_MICS=64, GEOMETRY_N_ARRAYS=1)
+    nat.configure_from(config)
+    directions.load_pad_from_geometry()
+    directions.load_lerp_from_geometry()
+    mics, n = directions.active_microphones()
+    d_mics = torch.from_numpy(nat.i32(mics)).cuda()
+    M = N = 256
+    M = 64
+    blocks = 1 << 16
+    gen = torch.Generator(device="cuda").manual_seed(1235)
+    sig = torch.empty((blocks, M, N), device="cuda")
+    for i in range(0, blocks, 8192):
+        sig[i:i + 8192].normal_(generator=gen)
+    out = torch.zeros((blocks, N), device="cuda")
+    off = (14 * 20 + 6) * n
+    res = {"workload": "C2: MISO steered beam, 64 mics, %d consecutive 256-sample blocks (%.1f GB resident, "
+                       "inputs larger than L2), /n*MIC_GAIN post-scale" % (blocks, blocks * M * N * 4 / 1e9)}
+    blk_bytes = n * N * 4 + 2 * n * 4 + N * 4
+    for name, algo in (("pad", nat.ALGO_PAD), ("lerp", nat.ALGO_LERP)):
+        ts = []
+        for i in range(8):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            nat.check(L.bf_miso_dev(algo, sig.data_ptr(), out.data_ptr(), blocks, d_mics.data_ptr(), n, off, 1, stream))
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = float(np.mean(ts[3:]))
+        gbs = blocks * blk_bytes / (ms * 1e-3) / 1e9
+        res[name] = {"samples_per_s": blocks * N / (ms * 1e-3), "x_realtime": blocks * N / (ms * 1e-3) / 48828.0,
+                     "gmac_per_s": blocks * n * N / (ms * 1e-3) / 1e9,
+                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": gbs / hbm_peak, "kernel": "miso_stream_kernel<%s>" % name,
+                                  "kernel_ms": ms, "algorithmic_bytes_per_launch": blocks * blk_bytes,
+                                  "traffic": None}}
+    del sig, out
+    return res
+
 # ----------------------------------------------------------------------------------------
 # the B200 arm
 # ----------------------------------------------------------------------------------------
@@ -408,30 +454,7 @@ def main():
         # ---- extra: BASELINE config C2, MISO stream (HBM-bound) ----------------------------
         if rank == 0:
             try:
-                blocks = 4096
-                n_m = 64
-                sig_m = torch.randn((blocks, M, N), generator=gen, device="cuda")
-                out_m = torch.zeros((blocks, N), device="cuda")
-                d_m64 = d_mics[:n_m].contiguous()
-                off = (D // 2) * n
-                ts = []
-                for i in range(8):
-                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record()
-                    nat.check(L.bf_miso_dev(algo, sig_m.data_ptr(), out_m.data_ptr(), blocks, d_m64.data_ptr(),
-                                            n_m, off, 1, stream))
-                    b.record()
-                    torch.cuda.synchronize()
-                    ts.append(a.elapsed_time(b))
-                ms = float(np.mean(ts[3:]))
-                blk_bytes = n_m * N * 4 + 2 * n_m * 4 + N * 4
-                gbs = blocks * blk_bytes / (ms * 1e-3) / 1e9
-                miso = {"workload": "C2: MISO, 64 mics, %d consecutive 256-sample blocks (%.2f GB, > L2), steer row + /n*MIC_GAIN" % (blocks, blocks * M * N * 4 / 1e9),
-                        "samples_per_s": blocks * N / (ms * 1e-3), "x_realtime": blocks * N / (ms * 1e-3) / 48828.0,
-                        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                                     "frac": gbs / hbm_peak, "kernel": "miso_stream_kernel", "kernel_ms": ms,
-                                     "traffic": None}}
-                del sig_m, out_m
+                miso = miso_c2(args, nat, L, config, directions, torch, stream, hbm_peak)
             except Exception as e:  # noqa: BLE001
                 miso = {"error": str(e)}
 

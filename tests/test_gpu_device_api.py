@@ -1,8 +1,6 @@
 """GPU: device-resident, batched and direction-sharded entry points (bf_mimo_dev, bf_miso_dev),
 the MISO stream kernel, the producer loops of lib.beamformer, and size-independent properties at
 the full BASELINE sizes.  PyTorch is used only to own device memory (tensor.data_ptr())."""
-import multiprocessing as mp
-
 import numpy as np
 import pytest
 
@@ -146,49 +144,25 @@ def test_full_size_c3_properties():
         assert bits_equal(out, g["miso_lerp"][i])
 
 
-def _producer(target_name, q, running, case):
-    import os, sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    sys.path.insert(0, os.path.join(root, "zybo-rt-sampler-image-detection_b200"))
-    sys.path.insert(0, root)
-    sys.path.insert(0, os.path.join(root, "tests"))
-    from util import gold, product_config
-    product_config(case)
-    from lib import beamformer
-    g = gold(case)
-    rec = np.concatenate([g["signals"], g["signals"][:, ::-1]], axis=1)
-    beamformer.connect(False, verbose=False, source=beamformer.ArraySource(rec))
-    getattr(beamformer, target_name)(q, running)
-
-
 @pytest.mark.parametrize("target", ["b", "uti_api"])
-def test_producer_loop_in_child_process(target):
+def test_producer_loop_in_child_process(target, tmp_path):
     """The reference runs its loops in multiprocessing.Process children created by fork
-    (main.pyx:702-721); CUDA must initialise lazily inside the child.  Payload contract: `b` puts
+    (main.pyx:702-721); CUDA must initialise lazily inside the child, so the scenario runs from a
+    fresh interpreter that never touched CUDA (tests/_loop_child.py).  Payload contract: `b` puts
     (power_map, frame_nr), the api loops put the bare map (camera.py:83, visual.py:421)."""
+    import os, subprocess, sys
     g = gold("c1")
-    ctx = mp.get_context("fork")
-    q, running = ctx.JoinableQueue(maxsize=4), ctx.Value("i", 1)
-    p = ctx.Process(target=_producer, args=(target, q, running, "c1"))
-    p.start()
-    try:
-        items = [q.get(timeout=120) for _ in range(3)]
-    finally:
-        running.value = 0
-        while True:
-            try:
-                q.get(timeout=2)
-            except Exception:  # noqa: BLE001
-                break
-        p.join(timeout=30)
-        if p.is_alive():
-            p.terminate()
-    first = items[0]
+    out = str(tmp_path / "loop.npz")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_loop_child.py")
+    subprocess.run([sys.executable, script, target, out], check=True, timeout=280)
+    z = np.load(out)
+    maps, nrs = z["maps"], z["nrs"]
     if target == "b":
-        assert isinstance(first, tuple) and first[1] == 1 and items[2][1] == 3
-        first = first[0]
-    assert first.shape == (20, 20) and first.dtype == np.float32 and first.flags["C_CONTIGUOUS"]
-    assert bits_equal(first.ravel(), g["img_pad"])
+        assert list(nrs) == [1, 2, 3]
+    else:
+        assert list(nrs) == [-1, -1, -1]
+    assert maps.shape == (3, 20, 20) and maps.dtype == np.float32 and z["contiguous"].all()
+    assert bits_equal(maps[0].ravel(), g["img_pad"])
 
 
 def test_miso_beam_listen_and_steering():

@@ -53,3 +53,17 @@ def product_config(case):
 def rel_err(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def float_table_equal(a, b):
+    """Bitwise equality of float tables, except that +0.0 and -0.0 are interchangeable.  The only
+    place they can differ is the on-axis direction of an odd x odd grid, where every raw delay is
+    +-0 and `x - min(x)` inherits the sign from whichever zero NumPy's SIMD min-reduction happened
+    to return on the build host; the integer table, the lerp split and every power map are
+    unaffected (documented in DESIGN.md)."""
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    if a.shape != b.shape or a.dtype != b.dtype:
+        return False
+    u = np.uint64 if a.dtype == np.float64 else np.uint32
+    same = a.view(u) == b.view(u)
+    return bool(np.all(same | ((a == 0) & (b == 0))))

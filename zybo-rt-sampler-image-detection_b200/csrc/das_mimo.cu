@@ -19,13 +19,18 @@
 //   * consecutive directions mostly share their integer delay for a microphone
 //     (the table varies slowly along the grid), so one shifted row load is
 //     reused for all directions of the group with the same delay: shared-memory
-//     traffic drops by ~R and the kernel becomes FP32-issue bound; the adds are
-//     issued as packed add.f32x2 / fma.f32x2 (FADD2/FFMA2)
+//     traffic drops by ~R and the kernel becomes FP32-pipe bound; the adds are
+//     issued as packed add.f32x2 / fma.f32x2 (FADD2/FFMA2: plain 3-register FADD
+//     only reaches half the FP32 rate on this SM, measured)
+//   * the table is re-laid out once per load into 16-byte "group entries" per
+//     (group, microphone), classified as UNIFORM (one delay for all 8 directions),
+//     TWO-RUN (delay changes once inside the group) or GENERAL; each warp copies its
+//     next 32 entries into a private shared-memory slot one chunk ahead and reads
+//     them back with a single broadcast LDS.128 per microphone
+//   * for pad the shifted row of microphone m+1 is loaded while microphone m is
+//     being accumulated (software pipeline, two register row buffers)
 //   * the epilogue reproduces out/n, square, in-order sum over t, /N exactly
 //     (exact_sum) or uses a warp-shuffle tree
-//
-// Tables are re-laid out once per load into "group entries" (8 x u16 byte offsets
-// per (group, mic), + 8 fp32 weights for lerp) read with one uniform 16-byte load.
 #include "bf_common.cuh"
 
 namespace bf {
@@ -35,12 +40,17 @@ static constexpr int kStages = 4;      // smem ring depth
 static constexpr int kMaxWarps = 15;   // consumer warps per CTA (+1 producer = 512 threads, 128 regs)
 static constexpr int kScratchStride = 68;
 
+enum { kGeneral = 0u, kUniform = 1u, kTwoRun = 2u };
+
 // ---------------------------------------------------------------------------
 // group-table builder
 // ---------------------------------------------------------------------------
 // One thread per (group, mic).  off = (P - w [- 1 for lerp]) * 4 bytes, so that
 // row_base + off + 4*t addresses sample (t - w [- 1]) of a row stored behind P
-// zeros.  Bit 0 of the first u16 flags "all 8 offsets equal".
+// zeros.  Offsets are multiples of 4: bits 1:0 of the first u16 carry the kind.
+//   GENERAL  x = o0|o1<<16, y = o2|o3<<16, z = o4|o5<<16, w = o6|o7<<16
+//   UNIFORM  x = o0|1
+//   TWO-RUN  x = o0|2 | ob<<16, y = split   (directions [0,split) use o0, the rest ob)
 __global__ void build_groups_kernel(const int *__restrict__ whole, const float *__restrict__ weight,
                                     uint4 *__restrict__ offs, float *__restrict__ wts, int n,
                                     int d_begin, int d_count, int groups, int P, int w_hi,
@@ -50,7 +60,6 @@ __global__ void build_groups_kernel(const int *__restrict__ whole, const float *
     if (idx >= groups * n) return;
     int g = idx / n, m = idx - g * n;
     uint32_t o[kR];
-    bool same = true;
 #pragma unroll
     for (int r = 0; r < kR; r++) {
         int dl = g * kR + r;
@@ -59,14 +68,24 @@ __global__ void build_groups_kernel(const int *__restrict__ whole, const float *
         int w = whole[e];
         w = w < 0 ? 0 : (w > w_hi ? w_hi : w);
         o[r] = (uint32_t)(P - w - (lerp ? 1 : 0)) * 4u;
-        if (o[r] != o[0]) same = false;
         if (lerp) wts[(size_t)idx * kR + r] = weight[e];
     }
+    int split = 1;
+    while (split < kR && o[split] == o[0]) split++;
+    bool two = split < kR;
+    for (int r = split; r < kR; r++)
+        if (o[r] != o[split < kR ? split : 0]) two = false;
     uint4 v;
-    v.x = (o[0] | (same ? 1u : 0u)) | (o[1] << 16);
-    v.y = o[2] | (o[3] << 16);
-    v.z = o[4] | (o[5] << 16);
-    v.w = o[6] | (o[7] << 16);
+    if (split == kR) {
+        v = make_uint4(o[0] | kUniform, 0u, 0u, 0u);
+    } else if (two) {
+        v = make_uint4(o[0] | kTwoRun | (o[split] << 16), (uint32_t)split, 0u, 0u);
+    } else {
+        v.x = o[0] | (o[1] << 16);
+        v.y = o[2] | (o[3] << 16);
+        v.z = o[4] | (o[5] << 16);
+        v.w = o[6] | (o[7] << 16);
+    }
     offs[idx] = v;
 }
 
@@ -76,10 +95,10 @@ static int build_groups(GroupTable &gt, const int *d_whole, const float *d_weigh
 {
     int groups = (d_count + kR - 1) / kR;
     size_t entries = (size_t)groups * n;
-    int rc = gt.offs.ensure(entries * sizeof(uint4));
+    int rc = gt.offs.ensure(entries * sizeof(uint4) + 512);     // +512: prefetch overrun pad
     if (rc) return rc;
     if (lerp) {
-        rc = gt.wts.ensure(entries * kR * sizeof(float));
+        rc = gt.wts.ensure(entries * kR * sizeof(float) + 1024);
         if (rc) return rc;
     }
     int w_hi = lerp ? n_samples - 1 : n_samples;
@@ -114,7 +133,7 @@ __global__ void diff_rows_kernel(const float *__restrict__ sig, const int *__res
 struct MimoParams {
     const float *sig;        // [frames][n_mics_total][N]
     const float *diff;       // [frames][n][N] (lerp only)
-    float *img;              // [frames][D_total]
+    float *img;              // output, see img_fs / img_ds
     const int *mic_ids;      // [n]
     const uint4 *offs;       // [groups][n]
     const float *wts;        // [groups][n][8]
@@ -124,7 +143,7 @@ struct MimoParams {
     int groups;              // groups per frame
     int tiles_per_frame, total_tiles;
     int W;                   // consumer warps
-    int Mt;                  // mic rows per stage
+    int Mt;                  // mic rows per stage (<= 32)
     int P;                   // zero floats in front of every row
     int n_pow2;              // n is a power of two -> exact reciprocal multiply
     float fn, inv_n;
@@ -140,17 +159,105 @@ __device__ __forceinline__ void load_row(const char *p, float2 (&v)[J / 2])
     }
 }
 
-template <int J, bool LERP, bool EXACT>
+// acc += a            (pad:  pad_and_sum.c:45)
+// acc += fma(h, b, a) (lerp: lerp_and_sum.c:54, b = s[i+1]-s[i]); PACK selects the packed
+// add.f32x2 / fma.f32x2 forms -- same IEEE rounding per element either way.
+template <bool LERP, bool PACK>
+__device__ __forceinline__ float2 das_accum(float2 acc, float2 a, float2 b, float h)
+{
+    if (PACK) {
+        if (LERP) return __fadd2_rn(acc, __ffma2_rn(make_float2(h, h), b, a));
+        return __fadd2_rn(acc, a);
+    }
+    if (LERP)
+        return make_float2(__fadd_rn(acc.x, __fmaf_rn(h, b.x, a.x)),
+                           __fadd_rn(acc.y, __fmaf_rn(h, b.y, a.y)));
+    return make_float2(__fadd_rn(acc.x, a.x), __fadd_rn(acc.y, a.y));
+}
+
+template <int J, bool LERP, bool PACK, int S>
+__device__ __forceinline__ void two_run(float2 (&acc)[kR][J / 2], const float2 (&a)[J / 2],
+                                        const float2 (&d)[J / 2], const float2 (&a2)[J / 2],
+                                        const float2 (&d2)[J / 2], const float (&h)[kR])
+{
+#pragma unroll
+    for (int r = 0; r < kR; r++)
+#pragma unroll
+        for (int q = 0; q < J / 2; q++)
+            acc[r][q] = (r < S) ? das_accum<LERP, PACK>(acc[r][q], a[q], d[q], h[r])
+                                : das_accum<LERP, PACK>(acc[r][q], a2[q], d2[q], h[r]);
+}
+
+// One microphone into the 8 accumulators of the group.  `a` holds the row at the
+// entry's first offset when PRE (prefetched by the caller), else it is loaded here.
+template <int J, bool LERP, bool PACK, bool PRE>
+__device__ __forceinline__ void process_mic(float2 (&acc)[kR][J / 2], const uint4 e,
+                                            const char *rowp, const size_t row_bytes,
+                                            float2 (&a)[J / 2], const float *wrow)
+{
+    const uint32_t kind = e.x & 3u;
+    const uint32_t oa = e.x & 0xfffcu;
+    float2 d[J / 2];
+    float h[kR];
+    if (!PRE) load_row<J>(rowp + oa, a);
+    if (LERP) {
+        load_row<J>(rowp + row_bytes + oa, d);
+        const float4 h0 = *(const float4 *)wrow, h1 = *(const float4 *)(wrow + 4);
+        h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w;
+        h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
+    }
+    if (kind == kUniform) {
+#pragma unroll
+        for (int r = 0; r < kR; r++)
+#pragma unroll
+            for (int q = 0; q < J / 2; q++)
+                acc[r][q] = das_accum<LERP, PACK>(acc[r][q], a[q], d[q], h[r]);
+    } else if (kind == kTwoRun) {
+        const uint32_t ob = e.x >> 16;
+        float2 a2[J / 2], d2[J / 2];
+        load_row<J>(rowp + ob, a2);
+        if (LERP) load_row<J>(rowp + row_bytes + ob, d2);
+        switch (e.y) {
+            case 1: two_run<J, LERP, PACK, 1>(acc, a, d, a2, d2, h); break;
+            case 2: two_run<J, LERP, PACK, 2>(acc, a, d, a2, d2, h); break;
+            case 3: two_run<J, LERP, PACK, 3>(acc, a, d, a2, d2, h); break;
+            case 4: two_run<J, LERP, PACK, 4>(acc, a, d, a2, d2, h); break;
+            case 5: two_run<J, LERP, PACK, 5>(acc, a, d, a2, d2, h); break;
+            case 6: two_run<J, LERP, PACK, 6>(acc, a, d, a2, d2, h); break;
+            default: two_run<J, LERP, PACK, 7>(acc, a, d, a2, d2, h); break;
+        }
+    } else {
+        // general: reload only when the delay changes from one direction to the next
+        const uint32_t ow[4] = {e.x, e.y, e.z, e.w};
+        uint32_t prev = oa;
+#pragma unroll
+        for (int r = 0; r < kR; r++) {
+            const uint32_t o = (r & 1) ? (ow[r >> 1] >> 16) : (ow[r >> 1] & 0xfffcu);
+            if (o != prev) {
+                load_row<J>(rowp + o, a);
+                if (LERP) load_row<J>(rowp + row_bytes + o, d);
+                prev = o;
+            }
+#pragma unroll
+            for (int q = 0; q < J / 2; q++)
+                acc[r][q] = das_accum<LERP, PACK>(acc[r][q], a[q], d[q], h[r]);
+        }
+    }
+}
+
+template <int J, bool LERP, bool EXACT, bool PACK>
 __global__ void __launch_bounds__((kMaxWarps + 1) * 32, 1) das_mimo_kernel(const MimoParams p)
 {
     constexpr int N = J * 32;
+    constexpr bool PIPE = !LERP;                         // row software pipeline (pad only)
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = p.W;
     const int RS = p.P + N;                              // row stride in floats
     const int arrays = LERP ? 2 : 1;
     const size_t row_bytes = (size_t)RS * 4;
-    const size_t stage_bytes = (size_t)p.Mt * arrays * row_bytes;
+    const size_t mic_bytes = arrays * row_bytes;         // one microphone's slot in a stage
+    const size_t stage_bytes = (size_t)p.Mt * mic_bytes;
 
     uint64_t *full = (uint64_t *)smem;                   // [kStages]
     uint64_t *empty = full + kStages;                    // [kStages]
@@ -194,7 +301,7 @@ __global__ void __launch_bounds__((kMaxWarps + 1) * 32, 1) das_mimo_kernel(const
                 unsigned char *sb = stages + (size_t)s * stage_bytes;
                 for (int r = lane; r < cnt; r += 32) {
                     const int mic = p.mic_ids[m0 + r];
-                    float *dst = (float *)(sb + (size_t)r * arrays * row_bytes) + p.P;
+                    float *dst = (float *)(sb + (size_t)r * mic_bytes) + p.P;
                     bfptx::bulk_g2s(dst, fsig + (size_t)mic * N, N * 4, &full[s]);
                     if (LERP)
                         bfptx::bulk_g2s(dst + RS, fdiff + (size_t)(m0 + r) * N, N * 4, &full[s]);
@@ -206,16 +313,40 @@ __global__ void __launch_bounds__((kMaxWarps + 1) * 32, 1) das_mimo_kernel(const
     }
 
     // ======================= consumer warps =================================
+    // per-warp shared slot: epilogue scratch, reused during the main loop as the
+    // entry buffer (uint4[32]) and, for lerp, the weight buffer (float[32][8])
     float *scratch = scratch_all + warp * (kR * kScratchStride);
+    uint4 *ebuf = (uint4 *)scratch;
+    float *wbuf = scratch + 128;
+
+    auto group_of = [&](int tile) {
+        const int frame = tile / p.tiles_per_frame;
+        return (tile - frame * p.tiles_per_frame) * W + warp;
+    };
+    // entries of chunk c of `tile` for this lane (one chunk ahead of their use)
+    uint4 e_pref = make_uint4(kUniform, 0u, 0u, 0u);
+    float4 w_pref0 = make_float4(0.f, 0.f, 0.f, 0.f), w_pref1 = w_pref0;
+    auto prefetch_entries = [&](int tile, int c) {
+        if (tile >= p.total_tiles) return;
+        const int g = group_of(tile);
+        if (g >= p.groups) return;
+        const int m = min(c * p.Mt + lane, p.n - 1);
+        const size_t idx = (size_t)g * p.n + m;
+        e_pref = __ldg(p.offs + idx);
+        if (LERP) {
+            const float4 *wp = (const float4 *)(p.wts + idx * kR);
+            w_pref0 = __ldg(wp);
+            w_pref1 = __ldg(wp + 1);
+        }
+    };
+    prefetch_entries(blockIdx.x, 0);
+
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int frame = tile / p.tiles_per_frame;
-        const int g = (tile - frame * p.tiles_per_frame) * W + warp;
+        const int g = group_of(tile);
         const bool active = g < p.groups;
-        const uint4 *offs = p.offs + (size_t)(active ? g : 0) * p.n;
-        const float4 *wts = LERP ? (const float4 *)(p.wts + (size_t)(active ? g : 0) * p.n * kR)
-                                 : nullptr;
 
         float2 acc[kR][J / 2];
 #pragma unroll
@@ -224,62 +355,41 @@ __global__ void __launch_bounds__((kMaxWarps + 1) * 32, 1) das_mimo_kernel(const
             for (int q = 0; q < J / 2; q++) acc[r][q] = make_float2(0.f, 0.f);
 
         for (int c = 0; c < nchunks; c++) {
-            const int m0 = c * p.Mt;
-            const int cnt = min(p.Mt, p.n - m0);
-            uint4 e_next = active ? __ldg(offs + m0) : make_uint4(0, 0, 0, 0);
+            const int cnt = min(p.Mt, p.n - c * p.Mt);
+            if (active) {
+                ebuf[lane] = e_pref;
+                if (LERP) {
+                    *(float4 *)(wbuf + lane * 8) = w_pref0;
+                    *(float4 *)(wbuf + lane * 8 + 4) = w_pref1;
+                }
+            }
+            __syncwarp();
+            if (c + 1 < nchunks) prefetch_entries(tile, c + 1);
+            else prefetch_entries(tile + gridDim.x, 0);
             bfptx::mbar_wait(&full[s], ph);
             if (active) {
                 const char *rowp = (const char *)(stages + (size_t)s * stage_bytes) + lane * 4;
-                for (int mm = 0; mm < cnt; mm++, rowp += arrays * row_bytes) {
-                    const uint4 e = e_next;
-                    if (mm + 1 < cnt) e_next = __ldg(offs + m0 + mm + 1);
-                    float h[kR];
-                    if (LERP) {
-                        const float4 h0 = __ldg(wts + (size_t)(m0 + mm) * 2);
-                        const float4 h1 = __ldg(wts + (size_t)(m0 + mm) * 2 + 1);
-                        h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w;
-                        h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
-                    }
-                    if (e.x & 1u) {
-                        // ---- fast path: one shifted row serves all 8 directions
-                        const uint32_t o = e.x & 0xfffcu;
-                        float2 a[J / 2], b[J / 2];
-                        load_row<J>(rowp + o, a);
-                        if (LERP) load_row<J>(rowp + row_bytes + o, b);
-#pragma unroll
-                        for (int r = 0; r < kR; r++) {
-                            const float2 hh = make_float2(h[r], h[r]);
-#pragma unroll
-                            for (int q = 0; q < J / 2; q++) {
-                                if (LERP)
-                                    acc[r][q] = __fadd2_rn(acc[r][q], __ffma2_rn(hh, b[q], a[q]));
-                                else
-                                    acc[r][q] = __fadd2_rn(acc[r][q], a[q]);
-                            }
+                if (PIPE) {
+                    float2 A[J / 2], B[J / 2];
+                    uint4 e0 = ebuf[0];
+                    load_row<J>(rowp + (e0.x & 0xfffcu), A);
+                    int mm = 0;
+                    for (; mm + 1 < cnt; mm += 2) {
+                        const uint4 e1 = ebuf[mm + 1];
+                        load_row<J>(rowp + mic_bytes + (e1.x & 0xfffcu), B);
+                        process_mic<J, LERP, PACK, true>(acc, e0, rowp, row_bytes, A, nullptr);
+                        if (mm + 2 < cnt) {
+                            e0 = ebuf[mm + 2];
+                            load_row<J>(rowp + 2 * mic_bytes + (e0.x & 0xfffcu), A);
                         }
-                    } else {
-                        // ---- general path: reload only when the delay changes
-                        const uint32_t ow[4] = {e.x & 0xfffcfffcu, e.y, e.z, e.w};
-                        uint32_t prev = 0xffffffffu;
-                        float2 a[J / 2], b[J / 2];
-#pragma unroll
-                        for (int r = 0; r < kR; r++) {
-                            const uint32_t o = (r & 1) ? (ow[r >> 1] >> 16) : (ow[r >> 1] & 0xffffu);
-                            if (o != prev) {
-                                load_row<J>(rowp + o, a);
-                                if (LERP) load_row<J>(rowp + row_bytes + o, b);
-                                prev = o;
-                            }
-                            const float2 hh = make_float2(h[r], h[r]);
-#pragma unroll
-                            for (int q = 0; q < J / 2; q++) {
-                                if (LERP)
-                                    acc[r][q] = __fadd2_rn(acc[r][q], __ffma2_rn(hh, b[q], a[q]));
-                                else
-                                    acc[r][q] = __fadd2_rn(acc[r][q], a[q]);
-                            }
-                        }
+                        process_mic<J, LERP, PACK, true>(acc, e1, rowp + mic_bytes, row_bytes, B, nullptr);
+                        rowp += 2 * mic_bytes;
                     }
+                    if (mm < cnt) process_mic<J, LERP, PACK, true>(acc, e0, rowp, row_bytes, A, nullptr);
+                } else {
+                    float2 A[J / 2];
+                    for (int mm = 0; mm < cnt; mm++, rowp += mic_bytes)
+                        process_mic<J, LERP, PACK, false>(acc, ebuf[mm], rowp, row_bytes, A, wbuf + mm * 8);
                 }
             }
             __syncwarp();
@@ -342,6 +452,7 @@ __global__ void __launch_bounds__((kMaxWarps + 1) * 32, 1) das_mimo_kernel(const
             for (int r = 0; r < kR; r++)
                 if (lane == r) mine = tot[r];
             if (lane < valid) img[lane * ds] = __fmul_rn(mine, 1.0f / (float)N);
+            __syncwarp();
         }
     }
 }
@@ -362,8 +473,13 @@ static int launch_J(bool lerp, bool exact, const MimoParams &mp, int grid, size_
         count_launch();
         return BF_OK;
     };
-    if (lerp) return exact ? go(das_mimo_kernel<J, true, true>) : go(das_mimo_kernel<J, true, false>);
-    return exact ? go(das_mimo_kernel<J, false, true>) : go(das_mimo_kernel<J, false, false>);
+    static const bool pack = getenv("BF_MIMO_PACKED") ? atoi(getenv("BF_MIMO_PACKED")) != 0 : true;
+    if (pack) {
+        if (lerp) return exact ? go(das_mimo_kernel<J, true, true, true>) : go(das_mimo_kernel<J, true, false, true>);
+        return exact ? go(das_mimo_kernel<J, false, true, true>) : go(das_mimo_kernel<J, false, false, true>);
+    }
+    if (lerp) return exact ? go(das_mimo_kernel<J, true, true, false>) : go(das_mimo_kernel<J, true, false, false>);
+    return exact ? go(das_mimo_kernel<J, false, true, false>) : go(das_mimo_kernel<J, false, false, false>);
 }
 
 int mimo_tiled(int algo, const float *d_sig, float *d_img, int frames, const int *d_mics, int n,
@@ -426,7 +542,7 @@ int mimo_tiled(int algo, const float *d_sig, float *d_img, int frames, const int
     mp.total_tiles = mp.tiles_per_frame * frames;
     int grid = mp.total_tiles < S.sm_count ? mp.total_tiles : S.sm_count;
 
-    // stage geometry: as many mic rows per stage as fit in the smem budget
+    // stage geometry: as many mic rows per stage as fit in the smem budget (<= 32: one entry per lane)
     const size_t row_bytes = (size_t)(P + N) * 4 * (lerp ? 2 : 1);
     const size_t scratch_bytes = (size_t)W * kR * kScratchStride * 4;
     const size_t budget = 227 * 1024 - 128 - scratch_bytes - 1024;

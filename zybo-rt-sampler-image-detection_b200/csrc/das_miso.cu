@@ -7,19 +7,18 @@
 // reference zero-pads every block, no history), so the batch is the grid.
 //
 // This path has 0.25 add per byte: it is HBM-bound.  Design: persistent CTAs, one
-// per SM; a producer warp streams whole microphone rows (1 KiB each at N = 256)
-// with 1-D bulk TMA copies into a 3-stage shared-memory ring (up to 64 KiB per
-// stage -> ~190 KiB of loads in flight per SM); N consumer threads each own one
-// output sample and add the delayed rows in table order (bit-identical to the
-// reference), then store the block with coalesced writes.
+// per SM; a producer warp streams microphone rows with 1-D bulk TMA copies
+// (cp.async.bulk -> SASS UBLKCP) into a ring of shared-memory stages of up to 32
+// rows each; runs of consecutive microphone ids in the adaptive array are fetched
+// with ONE copy (a fully populated array is a single 32 KiB copy per stage), which
+// matters because every bulk copy carries a fixed issue cost.  N consumer threads
+// each own one output sample and add the delayed rows in table order
+// (bit-identical to the reference), then store the block with coalesced writes.
 #include "bf_common.cuh"
 
 namespace bf {
 
-int miso_simple(int algo, const float *d_sig, float *d_out, int blocks, const int *d_mics, int n,
-                int offset, int by_mic_id, int scale, cudaStream_t st);
-
-static constexpr int kMisoStages = 3;
+static constexpr int kMisoMaxStages = 8;
 
 struct MisoParams {
     const float *sig;      // [blocks][n_mics_total][N]
@@ -27,7 +26,7 @@ struct MisoParams {
     const int *mic_ids;    // [n]
     const int *whole;      // table row (already offset), [n]
     const float *weight;   // lerp weights row, [n]
-    int n, n_mics_total, N, blocks, Mt;
+    int n, n_mics_total, N, blocks, Mt, stages;
     int scale;
     float fn, gain;
 };
@@ -37,26 +36,26 @@ __global__ void __launch_bounds__(512 + 32, 1) miso_stream_kernel(const MisoPara
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int N = p.N;
-    const int nthreads_c = N;                       // consumer threads (multiple of 32)
-    const int cwarps = nthreads_c >> 5;
+    const int cwarps = N >> 5;                      // consumer warps (N threads)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint64_t *full = (uint64_t *)smem;
-    uint64_t *empty = full + kMisoStages;
-    int *s_w = (int *)(smem + 128);                 // [n]
-    float *s_h = (float *)(s_w + p.n);              // [n]
-    int *s_mic = (int *)(s_h + p.n);                // [n]
-    const size_t tab_bytes = ((size_t)p.n * 12 + 127) / 128 * 128;
+    uint64_t *full = (uint64_t *)smem;              // [kMisoMaxStages]
+    uint64_t *empty = full + kMisoMaxStages;        // [kMisoMaxStages]
+    const int npad = (p.n + 3) & ~3;
+    int *s_w = (int *)(smem + 128);                 // [npad]
+    float *s_h = (float *)(s_w + npad);             // [npad]
+    int *s_mic = (int *)(s_h + npad);               // [npad]
+    const size_t tab_bytes = ((size_t)npad * 12 + 127) / 128 * 128;
     unsigned char *stages = smem + 128 + tab_bytes;
     const size_t stage_bytes = (size_t)p.Mt * N * 4;
 
-    for (int m = threadIdx.x; m < p.n; m += blockDim.x) {
-        int w = p.whole[m];
+    for (int m = threadIdx.x; m < npad; m += blockDim.x) {
+        int w = m < p.n ? p.whole[m] : N;           // pad entries: delay N = no contribution
         s_w[m] = w < 0 ? 0 : w;
-        s_h[m] = LERP ? p.weight[m] : 0.0f;
-        s_mic[m] = p.mic_ids[m];
+        s_h[m] = (LERP && m < p.n) ? p.weight[m] : 0.0f;
+        s_mic[m] = m < p.n ? p.mic_ids[m] : 0;
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kMisoStages; s++) {
+        for (int s = 0; s < p.stages; s++) {
             bfptx::mbar_init(&full[s], 1);
             bfptx::mbar_init(&empty[s], cwarps);
         }
@@ -74,14 +73,24 @@ __global__ void __launch_bounds__(512 + 32, 1) miso_stream_kernel(const MisoPara
             const float *bs = p.sig + (size_t)b * p.n_mics_total * N;
             for (int c = 0; c < nchunks; c++) {
                 const int m0 = c * p.Mt, cnt = min(p.Mt, p.n - m0);
+                // lane r owns row r of the chunk; a lane is a run head when its microphone
+                // does not directly follow the previous row's -> one copy per run
+                const bool in = lane < cnt;
+                const int mic = in ? s_mic[m0 + lane] : -2;
+                const int prev = __shfl_up_sync(0xffffffffu, mic, 1);
+                const bool head = in && (lane == 0 || mic != prev + 1);
+                const unsigned heads = __ballot_sync(0xffffffffu, head);
                 bfptx::mbar_wait(&empty[s], ph);
                 if (lane == 0) bfptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(cnt * N * 4));
                 __syncwarp();
-                float *sb = (float *)(stages + (size_t)s * stage_bytes);
-                for (int r = lane; r < cnt; r += 32)
-                    bfptx::bulk_g2s(sb + (size_t)r * N, bs + (size_t)s_mic[m0 + r] * N, N * 4,
-                                    &full[s]);
-                if (++s == kMisoStages) { s = 0; ph ^= 1; }
+                if (head) {
+                    const unsigned rest = lane == 31 ? 0u : (heads >> (lane + 1));
+                    const int next = rest ? lane + __ffs(rest) : cnt;
+                    float *sb = (float *)(stages + (size_t)s * stage_bytes);
+                    bfptx::bulk_g2s(sb + (size_t)lane * N, bs + (size_t)mic * N,
+                                    (uint32_t)((next - lane) * N * 4), &full[s]);
+                }
+                if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
         return;
@@ -97,23 +106,35 @@ __global__ void __launch_bounds__(512 + 32, 1) miso_stream_kernel(const MisoPara
             const int m0 = c * p.Mt, cnt = min(p.Mt, p.n - m0);
             bfptx::mbar_wait(&full[s], ph);
             const float *sb = (const float *)(stages + (size_t)s * stage_bytes);
-#pragma unroll 4
-            for (int mm = 0; mm < cnt; mm++) {
-                const float *row = sb + (size_t)mm * N;
+            // 4 microphones per step: one 16-byte broadcast load of their delays (+ weights)
+            for (int mm = 0; mm < cnt; mm += 4) {
+                const int4 w4 = *(const int4 *)(s_w + m0 + mm);
+                const int wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                float hv[4] = {0.f, 0.f, 0.f, 0.f};
                 if (LERP) {
-                    const int i = t - s_w[m0 + mm] - 1;          // lerp_and_sum.c:52-55
-                    if (i >= 0) {
-                        const float a = row[i], bb = row[i + 1];
-                        acc = __fadd_rn(acc, __fmaf_rn(s_h[m0 + mm], __fsub_rn(bb, a), a));
+                    const float4 h4 = *(const float4 *)(s_h + m0 + mm);
+                    hv[0] = h4.x; hv[1] = h4.y; hv[2] = h4.z; hv[3] = h4.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (mm + k < cnt) {
+                        const float *row = sb + (size_t)(mm + k) * N;
+                        if (LERP) {
+                            const int i = t - wv[k] - 1;             // lerp_and_sum.c:52-55
+                            if (i >= 0) {
+                                const float a = row[i], bb = row[i + 1];
+                                acc = __fadd_rn(acc, __fmaf_rn(hv[k], __fsub_rn(bb, a), a));
+                            }
+                        } else {
+                            const int i = t - wv[k];                 // pad_and_sum.c:43-46
+                            if (i >= 0) acc = __fadd_rn(acc, row[i]);
+                        }
                     }
-                } else {
-                    const int i = t - s_w[m0 + mm];              // pad_and_sum.c:43-46
-                    if (i >= 0) acc = __fadd_rn(acc, row[i]);
                 }
             }
             __syncwarp();
             if (lane == 0) bfptx::mbar_arrive(&empty[s]);
-            if (++s == kMisoStages) { s = 0; ph ^= 1; }
+            if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         if (p.scale) acc = __fmul_rn(__fdiv_rn(acc, p.fn), p.gain);   // api.c:519-523
         p.out[(size_t)b * N + t] = acc;
@@ -127,7 +148,7 @@ int miso_run(int algo, const float *d_sig, float *d_out, int blocks, const int *
     const int N = S.cfg.n_samples;
     const bool streamable = (algo == BF_ALGO_PAD || algo == BF_ALGO_LERP) && !by_mic_id &&
                             !S.simple_kernel && N % 32 == 0 && N >= 32 && N <= 512 &&
-                            blocks >= 8 && (((uintptr_t)d_sig & 15) == 0) && (N * 4) % 16 == 0;
+                            blocks >= 8 && (((uintptr_t)d_sig & 15) == 0);
     if (!streamable)
         return miso_simple(algo, d_sig, d_out, blocks, d_mics, n, offset, by_mic_id, scale, st);
 
@@ -147,16 +168,20 @@ int miso_run(int algo, const float *d_sig, float *d_out, int blocks, const int *
     mp.n = n; mp.n_mics_total = S.cfg.n_microphones; mp.N = N; mp.blocks = blocks;
     mp.scale = scale; mp.fn = (float)n; mp.gain = S.cfg.mic_gain;
 
-    const size_t tab_bytes = ((size_t)n * 12 + 127) / 128 * 128;
+    const int npad = (n + 3) & ~3;
+    const size_t tab_bytes = ((size_t)npad * 12 + 127) / 128 * 128;
     const size_t budget = 227 * 1024 - 128 - tab_bytes - 1024;
-    int Mt = n;
-    while (Mt > 1 && (size_t)Mt * N * 4 * kMisoStages > budget) Mt = (Mt + 1) / 2;
-    if ((size_t)Mt * N * 4 * kMisoStages > budget) {
+    // stages of up to 32 rows (one producer lane per row, multiple of 4 rows), as many as fit
+    int Mt = npad < 32 ? npad : 32;
+    while (Mt > 4 && (size_t)Mt * N * 4 * 2 > budget) Mt -= 4;
+    int stages = (int)(budget / ((size_t)Mt * N * 4));
+    if (stages > kMisoMaxStages) stages = kMisoMaxStages;
+    if (stages < 2) {
         set_error(BF_ERR_CONFIG, "miso: shared memory budget exceeded");
         return BF_ERR_CONFIG;
     }
-    mp.Mt = Mt;
-    const size_t smem = 128 + tab_bytes + (size_t)kMisoStages * Mt * N * 4;
+    mp.Mt = Mt; mp.stages = stages;
+    const size_t smem = 128 + tab_bytes + (size_t)stages * Mt * N * 4;
     const int grid = blocks < S.sm_count ? blocks : S.sm_count;
     if (algo == BF_ALGO_LERP) {
         BF_CUDA(cudaFuncSetAttribute(miso_stream_kernel<true>,

@@ -12,7 +12,7 @@ def plot_py_stimulus(n_mics, n_samples, fs=48828, frequency=8000):
     time = np.arange(0, 1, 1 / fs)
     wave = (1 * np.sin(2 * np.pi * frequency * time + 0))[:n_samples]
     sig = np.repeat(wave, n_mics, axis=0).reshape((n_samples, n_mics)).T
-    return np.float32(sig)
+    return np.ascontiguousarray(sig, dtype=np.float32)   # (PC/plot.py returns the transposed view)
 
 
 def point_sources(delays, mic_ids, n_mics_total, n_samples, fs, sources, noise_sigma, seed,

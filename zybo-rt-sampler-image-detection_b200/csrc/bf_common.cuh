@@ -59,6 +59,7 @@ struct GroupTable {            // device-friendly re-layout, built lazily per (n
     DevBuf wts;                // float [groups][n][8] (lerp weights), lerp only
     int n = -1, d_begin = -1, d_count = -1, pad = -1, n_samples = -1;
     int groups = 0;
+    int R = 0;                 // directions per group the layout was built for
 };
 
 struct Tables {

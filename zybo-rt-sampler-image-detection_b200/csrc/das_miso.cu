@@ -18,7 +18,7 @@
 
 namespace bf {
 
-static constexpr int kMisoMaxStages = 8;
+static constexpr int kMisoMaxStages = 16;   // barriers live in the first 256 bytes of smem
 
 struct MisoParams {
     const float *sig;      // [blocks][n_mics_total][N]
@@ -27,6 +27,7 @@ struct MisoParams {
     const int *whole;      // table row (already offset), [n]
     const float *weight;   // lerp weights row, [n]
     int n, n_mics_total, N, blocks, Mt, stages;
+    int copy_rows;         // max rows per bulk copy (run splitting)
     int scale;
     float fn, gain;
 };
@@ -41,11 +42,11 @@ __global__ void __launch_bounds__(512 + 32, 1) miso_stream_kernel(const MisoPara
     uint64_t *full = (uint64_t *)smem;              // [kMisoMaxStages]
     uint64_t *empty = full + kMisoMaxStages;        // [kMisoMaxStages]
     const int npad = (p.n + 3) & ~3;
-    int *s_w = (int *)(smem + 128);                 // [npad]
+    int *s_w = (int *)(smem + 256);                 // [npad]
     float *s_h = (float *)(s_w + npad);             // [npad]
     int *s_mic = (int *)(s_h + npad);               // [npad]
     const size_t tab_bytes = ((size_t)npad * 12 + 127) / 128 * 128;
-    unsigned char *stages = smem + 128 + tab_bytes;
+    unsigned char *stages = smem + 256 + tab_bytes;
     const size_t stage_bytes = (size_t)p.Mt * N * 4;
 
     for (int m = threadIdx.x; m < npad; m += blockDim.x) {
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(512 + 32, 1) miso_stream_kernel(const MisoPara
                 const bool in = lane < cnt;
                 const int mic = in ? s_mic[m0 + lane] : -2;
                 const int prev = __shfl_up_sync(0xffffffffu, mic, 1);
-                const bool head = in && (lane == 0 || mic != prev + 1);
+                const bool head = in && (lane == 0 || mic != prev + 1 || (lane % p.copy_rows) == 0);
                 const unsigned heads = __ballot_sync(0xffffffffu, head);
                 bfptx::mbar_wait(&empty[s], ph);
                 if (lane == 0) bfptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(cnt * N * 4));
@@ -170,18 +171,22 @@ int miso_run(int algo, const float *d_sig, float *d_out, int blocks, const int *
 
     const int npad = (n + 3) & ~3;
     const size_t tab_bytes = ((size_t)npad * 12 + 127) / 128 * 128;
-    const size_t budget = 227 * 1024 - 128 - tab_bytes - 1024;
+    const size_t budget = 227 * 1024 - 256 - tab_bytes - 1024;
     // stages of up to 32 rows (one producer lane per row, multiple of 4 rows), as many as fit
     int Mt = npad < 32 ? npad : 32;
+    if (const char *e = getenv("BF_MISO_MT")) { int v = atoi(e) & ~3; if (v >= 4 && v <= Mt) Mt = v; }
     while (Mt > 4 && (size_t)Mt * N * 4 * 2 > budget) Mt -= 4;
     int stages = (int)(budget / ((size_t)Mt * N * 4));
     if (stages > kMisoMaxStages) stages = kMisoMaxStages;
+    if (const char *e = getenv("BF_MISO_STAGES")) { int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }
+    mp.copy_rows = 32;
+    if (const char *e = getenv("BF_MISO_COPY_ROWS")) { int v = atoi(e); if (v >= 1 && v <= 32) mp.copy_rows = v; }
     if (stages < 2) {
         set_error(BF_ERR_CONFIG, "miso: shared memory budget exceeded");
         return BF_ERR_CONFIG;
     }
     mp.Mt = Mt; mp.stages = stages;
-    const size_t smem = 128 + tab_bytes + (size_t)stages * Mt * N * 4;
+    const size_t smem = 256 + tab_bytes + (size_t)stages * Mt * N * 4;
     const int grid = blocks < S.sm_count ? blocks : S.sm_count;
     if (algo == BF_ALGO_LERP) {
         BF_CUDA(cudaFuncSetAttribute(miso_stream_kernel<true>,

@@ -163,6 +163,15 @@ int bf_mimo_dev_ex(int algo, const float *d_signals, float *d_images, int frames
 int bf_miso_dev(int algo, const float *d_signals, float *d_out, int blocks,
                 const int *d_mic_ids, int n, int offset, int scale, void *stream);
 
+/* ---- batch replay with HOST buffers (BASELINE config C5: recorded streams) ---------
+ * signals float [frames][n_microphones][n_samples], images float [frames][D], both HOST
+ * pointers (pageable or pinned; pinned buffers are copied without staging).  Frames are
+ * processed in chunks: the host-to-device copy of chunk k+1 and the device-to-host copy of
+ * chunk k-1 overlap the kernel of chunk k (three streams).  Returns when `images` is
+ * complete.  Same result as `frames` successive mimo_pad / mimo_lerp calls. */
+int bf_mimo_host_batch(int algo, const float *signals, float *images, int frames,
+                       const int *adaptive_array, int n);
+
 /* ---- tables straight from device memory -------------------------------
  * algo PAD: d_table = int32 [count]; LERP/HYBRID: float32 delays [count];
  * FIR_*: float32 taps [count].  Same semantics as load_coefficients_*. */

@@ -183,3 +183,40 @@ def test_miso_beam_listen_and_steering():
         assert bits_equal(audio, ref)
     finally:
         beamformer.disconnect()
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("algo_name", ["pad", "lerp"])
+def test_host_batch_replay_equals_per_buffer_calls(algo_name, pinned):
+    """bf_mimo_host_batch (chunked, copies overlapped with the kernel on three streams) gives the
+    same maps as one mimo_pad/mimo_lerp call per buffer; pageable and pinned host memory."""
+    config, nat, L = _setup("c1")
+    torch = _torch()
+    from lib import directions
+    g = gold("c1")
+    mics = nat.i32(g["mic_ids"])
+    D, n, N, M = 400, 64, 256, 64
+    whole, d32 = directions.whole_and_f32()
+    L.load_coefficients_pad(nat.ptr(whole), whole.size)
+    L.load_coefficients_lerp(nat.ptr(d32), d32.size)
+    nat.check()
+    F = 37                                            # 16 + 16 + 5: three chunks, ragged tail
+    rng = np.random.default_rng(21)
+    frames = rng.standard_normal((F, M, N)).astype(np.float32)
+    frames[3] = g["signals"]
+    algo = nat.ALGO_PAD if algo_name == "pad" else nat.ALGO_LERP
+    name = "mimo_pad" if algo_name == "pad" else "mimo_lerp"
+    single = np.zeros((F, D), np.float32)
+    for f in range(F):
+        getattr(L, name)(nat.ptr(frames[f]), nat.ptr(single[f]), nat.ptr(mics), n)
+        nat.check()
+    assert bits_equal(single[3], g["img_pad" if algo_name == "pad" else "img_lerp"])
+    if pinned:
+        h_in = torch.from_numpy(frames).pin_memory()
+        h_out = torch.zeros((F, D), dtype=torch.float32).pin_memory()
+        nat.check(L.bf_mimo_host_batch(algo, h_in.data_ptr(), h_out.data_ptr(), F, nat.ptr(mics), n))
+        got = h_out.numpy()
+    else:
+        got = np.full((F, D), np.nan, np.float32)
+        nat.check(L.bf_mimo_host_batch(algo, nat.ptr(frames), nat.ptr(got), F, nat.ptr(mics), n))
+    assert bits_equal(got, single)

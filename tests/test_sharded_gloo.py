@@ -1,0 +1,77 @@
+"""CPU: the N > 1 path (direction sharding + one in-place all-gather) with world_size = 2 over
+gloo.  The per-rank slice is computed by the oracle here (tests may use it); on GPUs the same
+ShardedMaps object is filled by one bf_mimo_dev_ex launch per rank (bench.py, test_gpu_*)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from util import ROOT, gold
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "zybo-rt-sampler-image-detection_b200"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from lib.sharded import ShardedMaps
+    from oracle import cpu
+    from util import gold
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = gold("ragged")                                  # D = 77: not divisible by 2
+    delays = g["delays"].reshape(77, -1)
+    whole = delays.astype(int).astype(np.int32)
+    n = whole.shape[1]
+    F = 3
+    rng = np.random.default_rng(3)
+    frames = rng.standard_normal((F, 256, 256)).astype(np.float32)
+    sm = ShardedMaps(77, F, rank, world, "cpu", dist)
+    rows = sm.my_rows()
+    for f in range(F):
+        full = cpu.mimo_pad(frames[f], g["mic_ids"], whole, 77)      # stand-in for the kernel
+        rows[:sm.d_count, f] = torch.from_numpy(full[sm.d_begin:sm.d_begin + sm.d_count])
+    maps = sm.gather()
+    np.save(os.path.join(out_dir, "rank%d.npy" % rank), maps.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_bounds_cover_grid_exactly():
+    sys.path.insert(0, os.path.join(ROOT, "zybo-rt-sampler-image-detection_b200"))
+    from lib.sharded import shard_bounds
+    for D in (1, 7, 77, 400, 1824, 32400):
+        for world in (1, 2, 3, 4, 8):
+            seen = np.zeros(D, int)
+            for r in range(world):
+                per, b, c = shard_bounds(D, world, r)
+                assert per * world >= D and 0 <= c <= per
+                seen[b:b + c] += 1
+            assert np.all(seen == 1)
+    assert shard_bounds(32400, 8, 3) == (4050, 12150, 4050)
+
+
+def test_two_rank_gather_assembles_the_map(tmp_path):
+    import torch.multiprocessing as tmp
+    from oracle import cpu
+    port = _free_port()
+    tmp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    g = gold("ragged")
+    whole = g["delays"].reshape(77, -1).astype(int).astype(np.int32)
+    rng = np.random.default_rng(3)
+    frames = rng.standard_normal((3, 256, 256)).astype(np.float32)
+    want = np.stack([cpu.mimo_pad(frames[f], g["mic_ids"], whole, 77) for f in range(3)], axis=1)
+    for r in range(2):
+        got = np.load(os.path.join(str(tmp_path), "rank%d.npy" % r))
+        assert got.shape == (77, 3) and np.array_equal(got, want)      # every rank holds the full map

@@ -46,8 +46,12 @@ def run(algo):
 L.bf_set_kernel_options(1, 1)
 print("simple kernel (no staging): pad %.0f GB/s  lerp %.0f GB/s" % (run(nat.ALGO_PAD), run(nat.ALGO_LERP)))
 L.bf_set_kernel_options(0, 1)
-for mt, st, cr in itertools.product((8, 16, 32), (2, 4, 7, 14), (1, 4, 32)):
+os.environ["BF_MISO_MODE"] = "direct"
+print("direct kernel (smem table, 8 loads in flight): pad %.0f GB/s  lerp %.0f GB/s" % (run(nat.ALGO_PAD), run(nat.ALGO_LERP)))
+os.environ["BF_MISO_MODE"] = "tma"
+for ctas, mt, st, cr in itertools.product((1, 2, 3, 4), (16, 32), (2, 3, 4, 7), (1, 32)):
     if cr > mt:
         continue
+    os.environ["BF_MISO_CTAS"] = str(ctas)
     os.environ["BF_MISO_MT"], os.environ["BF_MISO_STAGES"], os.environ["BF_MISO_COPY_ROWS"] = str(mt), str(st), str(cr)
-    print("Mt %2d stages %d copy_rows %2d: pad %.0f GB/s  lerp %.0f GB/s" % (mt, st, cr, run(nat.ALGO_PAD), run(nat.ALGO_LERP)), flush=True)
+    print("ctas %d Mt %2d stages %d copy_rows %2d: pad %.0f GB/s  lerp %.0f GB/s" % (ctas, mt, st, cr, run(nat.ALGO_PAD), run(nat.ALGO_LERP)), flush=True)

@@ -397,6 +397,83 @@ int bf_miso_dev(int algo, const float *d_signals, float *d_out, int blocks, cons
     return miso_run(algo, d_signals, d_out, blocks, d_mic_ids, n, offset, 0, scale, (cudaStream_t)stream);
 }
 
+int bf_mimo_host_batch(int algo, const float *signals, float *images, int frames,
+                       const int *adaptive_array, int n)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    clear_error();
+    State &S = state();
+    int rc = ensure_device();
+    if (rc) return rc;
+    if ((rc = check_n(n, "bf_mimo_host_batch"))) return rc;
+    if (frames < 1 || !signals || !images || !adaptive_array) {
+        set_error(BF_ERR_ARG, "bf_mimo_host_batch: frames %d", frames);
+        return BF_ERR_ARG;
+    }
+    const size_t sig_f = (size_t)S.cfg.n_microphones * S.cfg.n_samples;     // floats per frame
+    const int D = S.cfg.max_res_x * S.cfg.max_res_y;
+    const int chunk = frames < 16 ? frames : 16;
+    static cudaStream_t st_in = nullptr, st_run = nullptr, st_out = nullptr;
+    static cudaEvent_t ev_in[2], ev_run[2], ev_out[2];
+    static DevBuf d_sig[2], d_img[2];
+    if (!st_in) {
+        BF_CUDA(cudaStreamCreateWithFlags(&st_in, cudaStreamNonBlocking));
+        BF_CUDA(cudaStreamCreateWithFlags(&st_run, cudaStreamNonBlocking));
+        BF_CUDA(cudaStreamCreateWithFlags(&st_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            BF_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+            BF_CUDA(cudaEventCreateWithFlags(&ev_run[i], cudaEventDisableTiming));
+            BF_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    auto pinned = [](const void *p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool in_pinned = pinned(signals), out_pinned = pinned(images);
+    const size_t stage_in = in_pinned ? 0 : (size_t)chunk * sig_f * sizeof(float);
+    const size_t stage_out = out_pinned ? 0 : (size_t)chunk * D * sizeof(float);
+    if ((rc = ensure_pinned(2 * (stage_in + stage_out) + 256))) return rc;
+    char *h_in[2] = {(char *)S.h_pinned, (char *)S.h_pinned + stage_in};
+    char *h_out[2] = {(char *)S.h_pinned + 2 * stage_in, (char *)S.h_pinned + 2 * stage_in + stage_out};
+    for (int i = 0; i < 2; i++) {
+        if ((rc = d_sig[i].ensure((size_t)chunk * sig_f * sizeof(float)))) return rc;
+        if ((rc = d_img[i].ensure((size_t)chunk * D * sizeof(float)))) return rc;
+    }
+    if ((rc = upload_mics(adaptive_array, n))) return rc;
+    BF_CUDA(cudaStreamSynchronize(0));
+    const int nchunks = (frames + chunk - 1) / chunk;
+    auto drain = [&](int k) -> int {          // wait for chunk k's results, un-stage them
+        const int sl = k & 1, f0 = k * chunk, fc = (frames - f0) < chunk ? (frames - f0) : chunk;
+        BF_CUDA(cudaEventSynchronize(ev_out[sl]));
+        if (!out_pinned) memcpy(images + (size_t)f0 * D, h_out[sl], (size_t)fc * D * sizeof(float));
+        return BF_OK;
+    };
+    for (int k = 0; k < nchunks; k++) {
+        const int sl = k & 1, f0 = k * chunk, fc = (frames - f0) < chunk ? (frames - f0) : chunk;
+        if (k >= 2 && (rc = drain(k - 2))) return rc;                  // slot sl is free again
+        const float *src = signals + (size_t)f0 * sig_f;
+        if (!in_pinned) { memcpy(h_in[sl], src, (size_t)fc * sig_f * sizeof(float)); src = (const float *)h_in[sl]; }
+        BF_CUDA(cudaMemcpyAsync(d_sig[sl].p, src, (size_t)fc * sig_f * sizeof(float), cudaMemcpyHostToDevice, st_in));
+        BF_CUDA(cudaEventRecord(ev_in[sl], st_in));
+        BF_CUDA(cudaStreamWaitEvent(st_run, ev_in[sl], 0));
+        if ((rc = mimo_dispatch(algo, d_sig[sl].as<float>(), d_img[sl].as<float>(), fc, S.d_mic_ids.as<int>(), n,
+                                0, D, ImgLayout{0, 0, 0}, st_run)))
+            return rc;
+        BF_CUDA(cudaEventRecord(ev_run[sl], st_run));
+        BF_CUDA(cudaStreamWaitEvent(st_out, ev_run[sl], 0));
+        float *dst = out_pinned ? images + (size_t)f0 * D : (float *)h_out[sl];
+        BF_CUDA(cudaMemcpyAsync(dst, d_img[sl].p, (size_t)fc * D * sizeof(float), cudaMemcpyDeviceToHost, st_out));
+        BF_CUDA(cudaEventRecord(ev_out[sl], st_out));
+        // the next H2D into the other slot must not overtake the kernel still reading it
+        BF_CUDA(cudaStreamWaitEvent(st_in, ev_run[sl ^ 1], 0));
+    }
+    for (int k = nchunks > 2 ? nchunks - 2 : 0; k < nchunks; k++)
+        if ((rc = drain(k))) return rc;
+    return BF_OK;
+}
+
 int bf_load_table_dev(int algo, const void *d_table, size_t count)
 {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -14,6 +14,8 @@
 // matters because every bulk copy carries a fixed issue cost.  N consumer threads
 // each own one output sample and add the delayed rows in table order
 // (bit-identical to the reference), then store the block with coalesced writes.
+#include <string.h>
+
 #include "bf_common.cuh"
 
 namespace bf {
@@ -116,21 +118,24 @@ __global__ void __launch_bounds__(512 + 32, 1) miso_stream_kernel(const MisoPara
                     const float4 h4 = *(const float4 *)(s_h + m0 + mm);
                     hv[0] = h4.x; hv[1] = h4.y; hv[2] = h4.z; hv[3] = h4.w;
                 }
+                // branch-free: all loads of the step are issued first (index clamped into the
+                // row), the adds are selected away where the reference's loop does not reach
+                // (table padding beyond n carries delay N, i.e. never reaches)
+                float v[4], u[4];
+                int iv[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    if (mm + k < cnt) {
-                        const float *row = sb + (size_t)(mm + k) * N;
-                        if (LERP) {
-                            const int i = t - wv[k] - 1;             // lerp_and_sum.c:52-55
-                            if (i >= 0) {
-                                const float a = row[i], bb = row[i + 1];
-                                acc = __fadd_rn(acc, __fmaf_rn(hv[k], __fsub_rn(bb, a), a));
-                            }
-                        } else {
-                            const int i = t - wv[k];                 // pad_and_sum.c:43-46
-                            if (i >= 0) acc = __fadd_rn(acc, row[i]);
-                        }
-                    }
+                    const float *row = sb + (size_t)(mm + k) * N;
+                    iv[k] = t - wv[k] - (LERP ? 1 : 0);      // pad_and_sum.c:43-46 / lerp_and_sum.c:52-55
+                    const int ic = max(iv[k], 0);
+                    v[k] = row[ic];
+                    u[k] = LERP ? row[ic + 1] : 0.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float c = LERP ? __fmaf_rn(hv[k], __fsub_rn(u[k], v[k]), v[k]) : v[k];
+                    const float sum = __fadd_rn(acc, c);
+                    acc = iv[k] >= 0 ? sum : acc;
                 }
             }
             __syncwarp();
@@ -138,6 +143,51 @@ __global__ void __launch_bounds__(512 + 32, 1) miso_stream_kernel(const MisoPara
             if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         if (p.scale) acc = __fmul_rn(__fdiv_rn(acc, p.fn), p.gain);   // api.c:519-523
+        p.out[(size_t)b * N + t] = acc;
+    }
+}
+
+// Alternative without staging: one CTA per block of samples, thread t reads its delayed
+// sample of every microphone row straight from global memory (coalesced, 8 loads in flight
+// per thread), table row in shared memory.  Same arithmetic order as above.
+template <bool LERP>
+__global__ void __launch_bounds__(512) miso_direct_kernel(const MisoParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int N = p.N, t = threadIdx.x;
+    const int npad = (p.n + 7) & ~7;
+    int *s_w = (int *)smem;
+    float *s_h = (float *)(s_w + npad);
+    int *s_mic = (int *)(s_h + npad);
+    for (int m = t; m < npad; m += blockDim.x) {
+        int w = m < p.n ? p.whole[m] : N;
+        s_w[m] = w < 0 ? 0 : w;
+        s_h[m] = (LERP && m < p.n) ? p.weight[m] : 0.0f;
+        s_mic[m] = m < p.n ? p.mic_ids[m] : p.mic_ids[0];
+    }
+    __syncthreads();
+    for (int b = blockIdx.x; b < p.blocks; b += gridDim.x) {
+        const float *bs = p.sig + (size_t)b * p.n_mics_total * N;
+        float acc = 0.0f;
+        for (int m0 = 0; m0 < npad; m0 += 8) {
+            float v[8], u[8];
+            int iv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float *row = bs + (size_t)s_mic[m0 + k] * N;
+                iv[k] = t - s_w[m0 + k] - (LERP ? 1 : 0);
+                const int ic = max(iv[k], 0);
+                v[k] = __ldg(row + ic);
+                u[k] = LERP ? __ldg(row + ic + 1) : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float c = LERP ? __fmaf_rn(s_h[m0 + k], __fsub_rn(u[k], v[k]), v[k]) : v[k];
+                const float sum = __fadd_rn(acc, c);
+                acc = iv[k] >= 0 ? sum : acc;
+            }
+        }
+        if (p.scale) acc = __fmul_rn(__fdiv_rn(acc, p.fn), p.gain);
         p.out[(size_t)b * N + t] = acc;
     }
 }
@@ -169,15 +219,45 @@ int miso_run(int algo, const float *d_sig, float *d_out, int blocks, const int *
     mp.n = n; mp.n_mics_total = S.cfg.n_microphones; mp.N = N; mp.blocks = blocks;
     mp.scale = scale; mp.fn = (float)n; mp.gain = S.cfg.mic_gain;
 
+    if (const char *e = getenv("BF_MISO_MODE")) {
+        if (!strcmp(e, "direct") && N >= 2) {
+            const int np8 = (n + 7) & ~7;
+            const int per_sm = 2048 / N < 1 ? 1 : 2048 / N;
+            int grid = S.sm_count * per_sm;
+            if (grid > blocks) grid = blocks;
+            if (algo == BF_ALGO_LERP) miso_direct_kernel<true><<<grid, N, (size_t)np8 * 12, st>>>(mp);
+            else miso_direct_kernel<false><<<grid, N, (size_t)np8 * 12, st>>>(mp);
+            BF_CHECK_LAUNCH();
+            count_launch();
+            return BF_OK;
+        }
+    }
     const int npad = (n + 3) & ~3;
     const size_t tab_bytes = ((size_t)npad * 12 + 127) / 128 * 128;
-    const size_t budget = 227 * 1024 - 256 - tab_bytes - 1024;
+    // several CTAs per SM: the consumer is a chain of dependent shared-memory loads, so the
+    // kernel needs many resident warps to keep enough bulk copies in flight (measured)
+    // Measured on B200 (tools/miso_sweep.py, C2): contiguous microphone ids (one 32 KiB copy per
+    // stage) -> 2 CTAs/SM x 2 stages: 6.9 TB/s pad, 6.8 TB/s lerp; scattered ids (1 KiB copies)
+    // -> 3 CTAs/SM x 2 stages: 6.8 / 5.9 TB/s.
+    static const int *s_key_ptr = nullptr; static int s_key_n = -1; static bool s_contig = false;
+    if (s_key_ptr != d_mics || s_key_n != n) {
+        std::vector<int> h(n);
+        BF_CUDA(cudaMemcpy(h.data(), d_mics, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+        int breaks = 0;
+        for (int m = 1; m < n; m++) breaks += (h[m] != h[m - 1] + 1);
+        s_contig = breaks * 8 <= n;            // mostly runs of >= 8 rows
+        s_key_ptr = d_mics; s_key_n = n;
+    }
+    int ctas = s_contig ? 2 : 3;
+    while (ctas > 1 && (N + 32) * ctas > 2048) ctas--;
+    if (const char *e = getenv("BF_MISO_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 4 && (N + 32) * v <= 2048) ctas = v; }
+    const size_t budget = (size_t)(227 * 1024) / ctas - 1024 - 256 - tab_bytes - 1024;
     // stages of up to 32 rows (one producer lane per row, multiple of 4 rows), as many as fit
     int Mt = npad < 32 ? npad : 32;
     if (const char *e = getenv("BF_MISO_MT")) { int v = atoi(e) & ~3; if (v >= 4 && v <= Mt) Mt = v; }
     while (Mt > 4 && (size_t)Mt * N * 4 * 2 > budget) Mt -= 4;
     int stages = (int)(budget / ((size_t)Mt * N * 4));
-    if (stages > kMisoMaxStages) stages = kMisoMaxStages;
+    if (stages > 2) stages = 2;                // deeper rings measured no faster (consumer-paced)
     if (const char *e = getenv("BF_MISO_STAGES")) { int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }
     mp.copy_rows = 32;
     if (const char *e = getenv("BF_MISO_COPY_ROWS")) { int v = atoi(e); if (v >= 1 && v <= 32) mp.copy_rows = v; }
@@ -187,7 +267,7 @@ int miso_run(int algo, const float *d_sig, float *d_out, int blocks, const int *
     }
     mp.Mt = Mt; mp.stages = stages;
     const size_t smem = 256 + tab_bytes + (size_t)stages * Mt * N * 4;
-    const int grid = blocks < S.sm_count ? blocks : S.sm_count;
+    const int grid = blocks < S.sm_count * ctas ? blocks : S.sm_count * ctas;
     if (algo == BF_ALGO_LERP) {
         BF_CUDA(cudaFuncSetAttribute(miso_stream_kernel<true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -56,6 +56,7 @@ def lib():
     L.bf_mimo_dev.argtypes = [ci, vp, vp, ci, vp, ci, ci, ci, vp]
     L.bf_mimo_dev_ex.argtypes = [ci, vp, vp, ci, vp, ci, ci, ci, ctypes.c_long, ctypes.c_long, ci, vp]
     L.bf_miso_dev.argtypes = [ci, vp, vp, ci, vp, ci, ci, ci, vp]
+    L.bf_mimo_host_batch.argtypes = [ci, vp, vp, ci, vp, ci]
     L.bf_load_table_dev.argtypes = [ci, vp, cs]
     L.bf_generate_delays.argtypes = [ctypes.c_double, vp, ci, vp, ci, ctypes.c_double, vp, vp, ci,
                                      vp, vp, vp, ci]

@@ -198,6 +198,25 @@ int bf_get_lerp_tables(int *whole, float *weight, size_t count);
 /* ... and the hybrid split (hybrid_convolve_and_sum.c:161-180). */
 int bf_get_hybrid_tables(int *whole, float *taps, size_t count);
 
+/* ---- frequency-domain delay-and-sum (PC/application/realtime_scripts/) ---------------
+ * bf_fd_setup installs the scan grid and microphone geometry of
+ * calc_phase_shift_cartesian.py:8-50 (host computes the O(X+Y+M) arrays exactly as the
+ * reference; the (bin, mic, direction) phasor table is never materialised):
+ *   lo_bin/hi_bin   threshold_freq_{lower,upper}_idx (bins [lo, hi) of the rfft)
+ *   x_scan, y_scan  np.linspace scan axes;  z = config.Z
+ *   mic_x, mic_y    r_prime_all coordinates of all n_mics microphones
+ *   active          indices of the microphones used (phase_shift[:, active_mics])
+ * bf_fd_das: signals HOST float [frames][n_mics][n_samples] (the (M, N) buffer the reference
+ * transposes before the call, camera.py:72), heatmap HOST float [frames][res_x*res_y]:
+ * rfft -> band limit -> steer -> |.|^2 -> sum over bins -> (normalise != 0) P/max(P), or all
+ * zeros when max(P) < threshold (beam_forming_algorithm.py:50-63). */
+int bf_fd_setup(int n_mics, int n_samples, double fs, double c, int lo_bin, int hi_bin,
+                const double *x_scan, int res_x, const double *y_scan, int res_y, double z,
+                const double *mic_x, const double *mic_y, const int *active, int n_active);
+int bf_fd_das(const float *signals, float *heatmap, int frames, float threshold, int normalise);
+int bf_fd_das_dev(const float *d_signals, float *d_heatmap, int frames, float threshold,
+                  int normalise, void *stream);
+
 /* Counters for bench.py: kernels launched by this library since the last reset. */
 uint64_t bf_kernel_launches(int reset);
 

@@ -57,6 +57,10 @@ def lib():
     L.bf_mimo_dev_ex.argtypes = [ci, vp, vp, ci, vp, ci, ci, ci, ctypes.c_long, ctypes.c_long, ci, vp]
     L.bf_miso_dev.argtypes = [ci, vp, vp, ci, vp, ci, ci, ci, vp]
     L.bf_mimo_host_batch.argtypes = [ci, vp, vp, ci, vp, ci]
+    cd = ctypes.c_double
+    L.bf_fd_setup.argtypes = [ci, ci, cd, cd, ci, ci, vp, ci, vp, ci, cd, vp, vp, vp, ci]
+    L.bf_fd_das.argtypes = [vp, vp, ci, ctypes.c_float, ci]
+    L.bf_fd_das_dev.argtypes = [vp, vp, ci, ctypes.c_float, ci, vp]
     L.bf_load_table_dev.argtypes = [ci, vp, cs]
     L.bf_generate_delays.argtypes = [ctypes.c_double, vp, ci, vp, ci, ctypes.c_double, vp, vp, ci,
                                      vp, vp, vp, ci]

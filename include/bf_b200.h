@@ -217,6 +217,15 @@ int bf_fd_das(const float *signals, float *heatmap, int frames, float threshold,
 int bf_fd_das_dev(const float *d_signals, float *d_heatmap, int frames, float threshold,
                   int normalise, void *stream);
 
+/* ---- frequency-domain MVDR (Capon) map; geometry/band from bf_fd_setup ------------------
+ * Not in the reference (parity unpinned, see csrc/fd_mvdr.cu).  snapshots: float
+ * [K][n_mics][n_samples]; power: float [res_x*res_y] = sum over bins of
+ * 1 / Re(a^H R_f^-1 a), R_f = 1/K sum_k x_k x_k^H + loading * tr(R_f)/M * I. */
+int bf_fd_mvdr(const float *snapshots, float *power, int K, double loading);
+int bf_fd_mvdr_dev(const float *d_snapshots, float *d_power, int K, double loading, void *stream);
+/* loaded covariance of the last MVDR call: HOST double [bins][M][M][2] */
+int bf_fd_get_covariance(double *cov, size_t count);
+
 /* Counters for bench.py: kernels launched by this library since the last reset. */
 uint64_t bf_kernel_launches(int reset);
 

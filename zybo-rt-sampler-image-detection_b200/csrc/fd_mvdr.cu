@@ -1,0 +1,312 @@
+// fd_mvdr.cu -- frequency-domain MVDR (Capon) power map: SURVEY.md section 8 row a20.
+//
+// NOT in the reference (it only has frequency-domain DAS, fd_path.cu); parity for this file
+// is "unpinned": the oracle is the float64 NumPy restatement in tests/test_gpu_mvdr.py, which
+// follows the reference's conventions for the pieces the reference does define -- real FFT
+// along samples, no window, no scaling (beam_forming_algorithm.py:31-33) and the steering
+// phasor a_f(d)[m] = exp(-j k_f u[d,m]) (calc_phase_shift_cartesian.py:44-48).  The one
+// reference-pinned check is on the covariance: Re(a^H R a) averaged over snapshots must equal
+// the DAS power of fd_path.cu (tested).
+//
+//   X_k[f,m]  = rfft(snapshot_k[:,m])[lo:hi]                      K snapshots
+//   R_f       = 1/K sum_k x_k x_k^H  + delta * tr(R_f)/M * I      (diagonal loading)
+//   R_f       = L_f L_f^H            (Cholesky)
+//   P(d)      = sum_f 1 / Re(a^H R_f^-1 a) = sum_f 1 / || L_f^-1 a_f(d) ||^2
+//
+// Conditioning: cond(R_f) can reach M/delta, so the spectra, the covariance, the
+// factorisation and the triangular inverse are kept in float64 (a few GFLOP); only the
+// steering contraction Y = L^-1 A (8*D*M^2*F flops, 8.8 TFLOP at BASELINE config C4) runs in
+// reduced precision.  This file holds the first correct version of that contraction on the
+// CUDA cores (fp32); the tcgen05 version is the round-2 item.
+#include <math.h>
+
+#include "bf_common.cuh"
+
+namespace bf {
+
+// shared with fd_path.cu through accessor functions ------------------------------------------
+struct FdGeom { int n_mics, n_active, N, lo, hi, D; double fs, c; const double *u; const int *active; };
+int fd_geometry(FdGeom *g);     // fd_path.cu
+
+struct MvdrState {
+    DevBuf spec;      // double2 [K][F][M]
+    DevBuf cov;       // double2 [F][M][M]  (row-major, Hermitian), later overwritten by L (lower)
+    DevBuf linv;      // float2  [F][M][M]  L^-1, row-major, lower triangular
+    DevBuf sig, out;
+    int K = 0;
+};
+static MvdrState g_mv;
+
+// ---- float64 real FFT, bins [lo,hi): same Stockham scheme as fd_rfft_kernel -----------------
+__global__ void mvdr_rfft64_kernel(const float *__restrict__ sig, const int *__restrict__ active,
+                                   int n_active, int n_mics, int N, int logN, int lo, int hi,
+                                   double2 *__restrict__ spec)
+{
+    extern __shared__ double2 shd[];
+    double2 *a = shd, *b = shd + N;
+    const int m = blockIdx.x, k = blockIdx.y;
+    const float *row = sig + ((size_t)k * n_mics + active[m]) * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) a[i] = make_double2((double)row[i], 0.0);
+    __syncthreads();
+    int l = 1;
+    for (int s = 0; s < logN; s++, l <<= 1) {
+        const int half = N >> 1;
+        for (int i = threadIdx.x; i < half; i += blockDim.x) {
+            const int j = i / l, kk = i - j * l;
+            const double2 x0 = a[j * l + kk], x1 = a[j * l + kk + half];
+            double sn, cs;
+            sincospi(-(double)kk / (double)l, &sn, &cs);
+            const double2 t = make_double2(x1.x * cs - x1.y * sn, x1.x * sn + x1.y * cs);
+            b[2 * j * l + kk] = make_double2(x0.x + t.x, x0.y + t.y);
+            b[2 * j * l + kk + l] = make_double2(x0.x - t.x, x0.y - t.y);
+        }
+        __syncthreads();
+        double2 *tmp = a; a = b; b = tmp;
+    }
+    const int F = hi - lo;
+    for (int f = lo + threadIdx.x; f < hi; f += blockDim.x)
+        spec[((size_t)k * F + (f - lo)) * n_active + m] = a[f];
+}
+
+// ---- covariance R_f[i][j] = 1/K sum_k X_k[f,i] conj(X_k[f,j]) -------------------------------
+__global__ void mvdr_cov_kernel(const double2 *__restrict__ spec, int K, int F, int M,
+                                double2 *__restrict__ cov)
+{
+    const int f = blockIdx.z;
+    const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
+    if (i >= M || j >= M) return;
+    double re = 0.0, im = 0.0;
+    for (int k = 0; k < K; k++) {
+        const double2 a = spec[((size_t)k * F + f) * M + i], b = spec[((size_t)k * F + f) * M + j];
+        re += a.x * b.x + a.y * b.y;          // a * conj(b)
+        im += a.y * b.x - a.x * b.y;
+    }
+    cov[((size_t)f * M + i) * M + j] = make_double2(re / K, im / K);
+}
+
+// diagonal loading: R_ii += delta * tr(R)/M
+__global__ void mvdr_load_kernel(double2 *__restrict__ cov, int M, double delta)
+{
+    __shared__ double red[32];
+    double2 *R = cov + (size_t)blockIdx.x * M * M;
+    double tr = 0.0;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) tr += R[(size_t)i * M + i].x;
+    for (int s = 16; s > 0; s >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tr;
+    __syncthreads();
+    tr = 0.0;
+    for (int w = 0; w < (int)((blockDim.x + 31) / 32); w++) tr += red[w];
+    const double add = delta * tr / M;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) R[(size_t)i * M + i].x += add;
+}
+
+// ---- Cholesky R = L L^H in place (lower triangle of the row-major matrix), one CTA per bin;
+//      thread i owns row i.  Column by column (right-looking dot form). ----------------------
+__global__ void mvdr_chol_kernel(double2 *__restrict__ cov, int M, int *__restrict__ fail)
+{
+    double2 *R = cov + (size_t)blockIdx.x * M * M;
+    __shared__ double2 colj[1024];      // L[j][0..j) of the pivot row (M <= 1024)
+    __shared__ double pivot;
+    for (int j = 0; j < M; j++) {
+        for (int k = threadIdx.x; k < j; k += blockDim.x) colj[k] = R[(size_t)j * M + k];
+        __syncthreads();
+        for (int i = j + threadIdx.x; i < M; i += blockDim.x) {
+            double2 s = R[(size_t)i * M + j];
+            const double2 *Li = R + (size_t)i * M;
+            for (int k = 0; k < j; k++) {
+                const double2 a = Li[k], b = colj[k];     // s -= L[i][k] * conj(L[j][k])
+                s.x -= a.x * b.x + a.y * b.y;
+                s.y -= a.y * b.x - a.x * b.y;
+            }
+            if (i == j) {
+                if (!(s.x > 0.0)) { atomicExch(fail, 1); s.x = 1.0; }
+                pivot = sqrt(s.x);
+            }
+            R[(size_t)i * M + j] = s;                     // un-normalised; divided below
+        }
+        __syncthreads();
+        const double d = pivot;
+        for (int i = j + threadIdx.x; i < M; i += blockDim.x) {
+            double2 s = R[(size_t)i * M + j];
+            R[(size_t)i * M + j] = (i == j) ? make_double2(d, 0.0) : make_double2(s.x / d, s.y / d);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- Z = L^-1 (lower triangular), forward substitution; thread c owns column c; output
+//      float2 row-major [i][c] ---------------------------------------------------------------
+__global__ void mvdr_trinv_kernel(const double2 *__restrict__ chol, int M, float2 *__restrict__ linv,
+                                  double2 *__restrict__ work)
+{
+    const double2 *L = chol + (size_t)blockIdx.x * M * M;
+    double2 *Z = work + (size_t)blockIdx.x * M * M;          // float64 copy, row-major [i][c]
+    float2 *Zf = linv + (size_t)blockIdx.x * M * M;
+    for (int i = 0; i < M; i++) {
+        const double dii = L[(size_t)i * M + i].x;
+        for (int c = threadIdx.x; c < M; c += blockDim.x) {
+            double2 s = make_double2(c == i ? 1.0 : 0.0, 0.0);
+            if (c <= i) {
+                for (int k = c; k < i; k++) {                 // s -= L[i][k] * Z[k][c]
+                    const double2 a = L[(size_t)i * M + k], z = Z[(size_t)k * M + c];
+                    s.x -= a.x * z.x - a.y * z.y;
+                    s.y -= a.x * z.y + a.y * z.x;
+                }
+                s.x /= dii; s.y /= dii;
+            } else {
+                s = make_double2(0.0, 0.0);
+            }
+            Z[(size_t)i * M + c] = s;
+            Zf[(size_t)i * M + c] = make_float2((float)s.x, (float)s.y);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- steering: P[d] = sum_f 1 / || L_f^-1 a_f(d) ||^2, CUDA-core fp32 --------------------------
+// CTA = TD directions; per bin the TD x M phasors are generated once into shared memory
+// ([m][d], float2), then rows of L^-1 stream through shared memory in chunks of RC rows.
+template <int TD, int RC>
+__global__ void __launch_bounds__(TD) mvdr_steer_kernel(const float2 *__restrict__ linv,
+                                                        const double *__restrict__ u, int M, int F,
+                                                        int lo, double bin_hz, double inv_c, int D,
+                                                        float *__restrict__ power)
+{
+    extern __shared__ float2 shm[];
+    float2 *ph = shm;                        // [M][TD]
+    float2 *rows = shm + (size_t)M * TD;     // [RC][M]
+    const int d = blockIdx.x * TD + threadIdx.x;
+    const bool ok = d < D;
+    const double *ud = u + (size_t)(ok ? d : 0) * M;
+    float total = 0.0f;
+    for (int f = 0; f < F; f++) {
+        const double turns_per_u = (double)(lo + f) * bin_hz * inv_c;
+        for (int m = 0; m < M; m++) {
+            const double turns = turns_per_u * ud[m];
+            const float fr = (float)(turns - rint(turns));
+            float sn, cs;
+            sincospif(-2.0f * fr, &sn, &cs);
+            ph[(size_t)m * TD + threadIdx.x] = make_float2(cs, sn);
+        }
+        const float2 *Lf = linv + (size_t)f * M * M;
+        float q = 0.0f;
+        for (int i0 = 0; i0 < M; i0 += RC) {
+            __syncthreads();
+            const int rc = min(RC, M - i0);
+            for (int e = threadIdx.x; e < rc * M; e += TD) rows[e] = Lf[(size_t)i0 * M + e];
+            __syncthreads();
+            for (int r = 0; r < rc; r++) {
+                const int i = i0 + r;
+                float yr = 0.0f, yi = 0.0f;
+                const float2 *Lr = rows + (size_t)r * M;
+                for (int j = 0; j <= i; j++) {                 // y_i = sum_{j<=i} Linv[i][j] a_j
+                    const float2 l = Lr[j], a = ph[(size_t)j * TD + threadIdx.x];
+                    yr = fmaf(l.x, a.x, fmaf(-l.y, a.y, yr));
+                    yi = fmaf(l.x, a.y, fmaf(l.y, a.x, yi));
+                }
+                q = fmaf(yr, yr, fmaf(yi, yi, q));
+            }
+        }
+        total += 1.0f / q;
+        __syncthreads();
+    }
+    if (ok) power[d] = total;
+}
+
+static int ilog2e(int n) { int l = 0; while ((1 << l) < n) l++; return (1 << l) == n ? l : -1; }
+
+int mvdr_dev(const float *d_snap, float *d_power, int K, double delta, cudaStream_t st)
+{
+    FdGeom G;
+    int rc = fd_geometry(&G);
+    if (rc) return rc;
+    const int M = G.n_active, F = G.hi - G.lo;
+    if (M > 1024) { set_error(BF_ERR_CONFIG, "mvdr: at most 1024 microphones"); return BF_ERR_CONFIG; }
+    MvdrState &S = g_mv;
+    if ((rc = S.spec.ensure((size_t)K * F * M * sizeof(double2)))) return rc;
+    if ((rc = S.cov.ensure((size_t)F * M * M * sizeof(double2)))) return rc;
+    if ((rc = S.linv.ensure((size_t)F * M * M * sizeof(float2)))) return rc;
+    DevBuf work, fail;
+    if ((rc = work.ensure((size_t)F * M * M * sizeof(double2)))) return rc;
+    if ((rc = fail.ensure(sizeof(int)))) { work.release(); return rc; }
+    cudaMemsetAsync(fail.p, 0, sizeof(int), st);
+    const int threads = G.N / 2 < 256 ? (G.N / 2 < 32 ? 32 : G.N / 2) : 256;
+    mvdr_rfft64_kernel<<<dim3(M, K), threads, 2 * G.N * sizeof(double2), st>>>(
+        d_snap, G.active, M, G.n_mics, G.N, ilog2e(G.N), G.lo, G.hi, S.spec.as<double2>());
+    mvdr_cov_kernel<<<dim3((M + 15) / 16, (M + 15) / 16, F), dim3(16, 16), 0, st>>>(
+        S.spec.as<double2>(), K, F, M, S.cov.as<double2>());
+    mvdr_load_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, delta);
+    S.K = K;
+    // keep a copy of the loaded covariance for bf_fd_get_covariance (work buffer is reused below)
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error(BF_ERR_CUDA, "mvdr: %s", cudaGetErrorString(e)); work.release(); fail.release(); return BF_ERR_CUDA; }
+    static DevBuf cov_copy;
+    if ((rc = cov_copy.ensure((size_t)F * M * M * sizeof(double2)))) { work.release(); fail.release(); return rc; }
+    cudaMemcpyAsync(cov_copy.p, S.cov.p, (size_t)F * M * M * sizeof(double2), cudaMemcpyDeviceToDevice, st);
+    mvdr_chol_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, fail.as<int>());
+    mvdr_trinv_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, S.linv.as<float2>(), work.as<double2>());
+    constexpr int TD = 64, RC = 8;
+    const size_t smem = ((size_t)M * TD + (size_t)RC * M) * sizeof(float2);
+    cudaFuncSetAttribute(mvdr_steer_kernel<TD, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const double bin_hz = (double)(int)((int)G.fs / 2) / (double)(G.N / 2);
+    mvdr_steer_kernel<TD, RC><<<(G.D + TD - 1) / TD, TD, smem, st>>>(S.linv.as<float2>(), G.u, M, F, G.lo,
+                                                                     bin_hz, 1.0 / G.c, G.D, d_power);
+    e = cudaStreamSynchronize(st);
+    int h_fail = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&h_fail, fail.p, sizeof(int), cudaMemcpyDeviceToHost);
+    // restore the covariance for inspection
+    cudaMemcpy(S.cov.p, cov_copy.p, (size_t)F * M * M * sizeof(double2), cudaMemcpyDeviceToDevice);
+    work.release(); fail.release();
+    count_launch(6);
+    if (e != cudaSuccess) { set_error(BF_ERR_CUDA, "mvdr: %s", cudaGetErrorString(e)); return BF_ERR_CUDA; }
+    if (h_fail) { set_error(BF_ERR_CONFIG, "mvdr: covariance not positive definite (increase loading)"); return BF_ERR_CONFIG; }
+    return BF_OK;
+}
+
+}  // namespace bf
+
+using namespace bf;
+
+extern "C" {
+
+int bf_fd_mvdr(const float *snapshots, float *power, int K, double loading)
+{
+    clear_error();
+    int rc = ensure_device();
+    if (rc) return rc;
+    FdGeom G;
+    if ((rc = fd_geometry(&G))) return rc;
+    if (!snapshots || !power || K < 1 || !(loading >= 0.0)) { set_error(BF_ERR_ARG, "bf_fd_mvdr: bad arguments"); return BF_ERR_ARG; }
+    MvdrState &S = g_mv;
+    const size_t sb = (size_t)K * G.n_mics * G.N * sizeof(float);
+    if ((rc = S.sig.ensure(sb))) return rc;
+    if ((rc = S.out.ensure((size_t)G.D * sizeof(float)))) return rc;
+    BF_CUDA(cudaMemcpy(S.sig.p, snapshots, sb, cudaMemcpyHostToDevice));
+    if ((rc = mvdr_dev(S.sig.as<float>(), S.out.as<float>(), K, loading, 0))) return rc;
+    BF_CUDA(cudaMemcpy(power, S.out.p, (size_t)G.D * sizeof(float), cudaMemcpyDeviceToHost));
+    return BF_OK;
+}
+
+int bf_fd_mvdr_dev(const float *d_snapshots, float *d_power, int K, double loading, void *stream)
+{
+    clear_error();
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!d_snapshots || !d_power || K < 1) { set_error(BF_ERR_ARG, "bf_fd_mvdr_dev: bad arguments"); return BF_ERR_ARG; }
+    return mvdr_dev(d_snapshots, d_power, K, loading, (cudaStream_t)stream);
+}
+
+// loaded covariance of the last bf_fd_mvdr call: HOST double [F][M][M][2] (re, im)
+int bf_fd_get_covariance(double *cov, size_t count)
+{
+    clear_error();
+    FdGeom G;
+    int rc = fd_geometry(&G);
+    if (rc) return rc;
+    const size_t have = (size_t)(G.hi - G.lo) * G.n_active * G.n_active;
+    if (!cov || count > have || g_mv.K == 0) { set_error(BF_ERR_NOT_LOADED, "no covariance (run bf_fd_mvdr first)"); return BF_ERR_NOT_LOADED; }
+    BF_CUDA(cudaMemcpy(cov, g_mv.cov.p, count * sizeof(double2), cudaMemcpyDeviceToHost));
+    return BF_OK;
+}
+
+}  // extern "C"

@@ -140,6 +140,16 @@ __global__ void fd_norm_kernel(float *__restrict__ power, int D, float threshold
     for (int i = threadIdx.x; i < D; i += blockDim.x) p[i] = quiet ? 0.0f : __fdiv_rn(p[i], mx);
 }
 
+// accessor for fd_mvdr.cu
+struct FdGeom { int n_mics, n_active, N, lo, hi, D; double fs, c; const double *u; const int *active; };
+int fd_geometry(FdGeom *g)
+{
+    if (g_fd.D == 0) { set_error(BF_ERR_NOT_LOADED, "fd: bf_fd_setup() has not been called"); return BF_ERR_NOT_LOADED; }
+    g->n_mics = g_fd.n_mics; g->n_active = g_fd.n_active; g->N = g_fd.N; g->lo = g_fd.lo; g->hi = g_fd.hi;
+    g->D = g_fd.D; g->fs = g_fd.fs; g->c = g_fd.c; g->u = g_fd.u.as<double>(); g->active = g_fd.active.as<int>();
+    return BF_OK;
+}
+
 static int ilog2_exact(int n)
 {
     int l = 0;

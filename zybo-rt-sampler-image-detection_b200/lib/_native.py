@@ -61,6 +61,9 @@ def lib():
     L.bf_fd_setup.argtypes = [ci, ci, cd, cd, ci, ci, vp, ci, vp, ci, cd, vp, vp, vp, ci]
     L.bf_fd_das.argtypes = [vp, vp, ci, ctypes.c_float, ci]
     L.bf_fd_das_dev.argtypes = [vp, vp, ci, ctypes.c_float, ci, vp]
+    L.bf_fd_mvdr.argtypes = [vp, vp, ci, cd]
+    L.bf_fd_mvdr_dev.argtypes = [vp, vp, ci, cd, vp]
+    L.bf_fd_get_covariance.argtypes = [vp, cs]
     L.bf_load_table_dev.argtypes = [ci, vp, cs]
     L.bf_generate_delays.argtypes = [ctypes.c_double, vp, ci, vp, ci, ctypes.c_double, vp, vp, ci,
                                      vp, vp, vp, ci]

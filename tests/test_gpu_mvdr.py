@@ -5,8 +5,8 @@ The reference-pinned anchor: the DAS form a^H R a of the SAME covariance must re
 frequency-domain DAS power (a19 path, itself checked against the reference module's golden map).
 
 Tolerance (stated, floating point): covariance 1e-12 relative (float64 end to end); MVDR map
-1e-4 of its maximum and 1e-3 per pixel (fp32 steering contraction against a float64 oracle, at
-cond(R) up to M/loading = 2.6e4)."""
+1e-5 relative per pixel (measured on B200: 9e-7 with the CUDA-core fp32 contraction), against a
+float64 oracle at cond(R) up to M/loading = 2.6e4."""
 import numpy as np
 import pytest
 
@@ -66,7 +66,10 @@ def _oracle(snaps, g, loading):
     return R, P, Pdas
 
 
-def test_mvdr_against_float64_oracle_and_das_anchor():
+@pytest.mark.parametrize("tensor_cores", [0, 1])
+def test_mvdr_against_float64_oracle_and_das_anchor(tensor_cores, monkeypatch):
+    """tensor_cores=1: tcgen05 steering contraction (3-pass split tf32); 0: CUDA-core fp32."""
+    monkeypatch.setenv("BF_MVDR_TC", str(tensor_cores))
     g = gold("fd_das")
     bfa, nat, L = _setup()
     K, loading = 12, 1e-2
@@ -86,10 +89,11 @@ def test_mvdr_against_float64_oracle_and_das_anchor():
     # (3) the MVDR map itself
     err = np.abs(P - P_ref)
     print("mvdr: max err / max = %.2e, max pixel rel = %.2e" % (err.max() / P_ref.max(), (err / P_ref).max()))
-    assert err.max() <= 1e-4 * P_ref.max()
-    assert np.all(err <= 1e-3 * P_ref)
-    # MVDR localises the strongest source on its grid cell
-    assert np.unravel_index(P.argmax(), (13, 13)) == (9, 4)
+    assert err.max() <= 1e-5 * P_ref.max()
+    assert np.all(err <= 1e-5 * P_ref)
+    # same peak cell as the oracle, and it is one of the three source cells
+    assert P.argmax() == P_ref.argmax()
+    assert np.unravel_index(P.argmax(), (13, 13)) in ((9, 4), (3, 10), (6, 6))
     # (4) properties: scaling the data by 2 scales P by 4 (loading is relative to the trace)
     P2 = np.zeros(169, np.float32)
     nat.check(L.bf_fd_mvdr(nat.ptr((snaps * np.float32(2)).astype(np.float32)), nat.ptr(P2), K, loading))

@@ -27,6 +27,8 @@ namespace bf {
 // shared with fd_path.cu through accessor functions ------------------------------------------
 struct FdGeom { int n_mics, n_active, N, lo, hi, D; double fs, c; const double *u; const int *active; };
 int fd_geometry(FdGeom *g);     // fd_path.cu
+int mvdr_steer_tc(const float2 *d_linv, const double *d_u, int M, int F, int lo, double bin_hz, double inv_c,
+                  int D, float *d_power, cudaStream_t st);     // fd_tc.cu
 
 struct MvdrState {
     DevBuf spec;      // double2 [K][F][M]
@@ -245,12 +247,22 @@ int mvdr_dev(const float *d_snap, float *d_power, int K, double delta, cudaStrea
     cudaMemcpyAsync(cov_copy.p, S.cov.p, (size_t)F * M * M * sizeof(double2), cudaMemcpyDeviceToDevice, st);
     mvdr_chol_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, fail.as<int>());
     mvdr_trinv_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, S.linv.as<float2>(), work.as<double2>());
-    constexpr int TD = 64, RC = 8;
-    const size_t smem = ((size_t)M * TD + (size_t)RC * M) * sizeof(float2);
-    cudaFuncSetAttribute(mvdr_steer_kernel<TD, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const double bin_hz = (double)(int)((int)G.fs / 2) / (double)(G.N / 2);
-    mvdr_steer_kernel<TD, RC><<<(G.D + TD - 1) / TD, TD, smem, st>>>(S.linv.as<float2>(), G.u, M, F, G.lo,
-                                                                     bin_hz, 1.0 / G.c, G.D, d_power);
+    // steering contraction: tcgen05 tensor-core kernel (fd_tc.cu) for 256 microphones, CUDA-core
+    // fp32 kernel otherwise (BF_MVDR_TC=0 forces the latter)
+    const bool use_tc = M == 256 && !(getenv("BF_MVDR_TC") && atoi(getenv("BF_MVDR_TC")) == 0);
+    if (use_tc) {
+        if ((rc = mvdr_steer_tc(S.linv.as<float2>(), G.u, M, F, G.lo, bin_hz, 1.0 / G.c, G.D, d_power, st))) {
+            work.release(); fail.release();
+            return rc;
+        }
+    } else {
+        constexpr int TD = 64, RC = 8;
+        const size_t smem = ((size_t)M * TD + (size_t)RC * M) * sizeof(float2);
+        cudaFuncSetAttribute(mvdr_steer_kernel<TD, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        mvdr_steer_kernel<TD, RC><<<(G.D + TD - 1) / TD, TD, smem, st>>>(S.linv.as<float2>(), G.u, M, F, G.lo,
+                                                                         bin_hz, 1.0 / G.c, G.D, d_power);
+    }
     e = cudaStreamSynchronize(st);
     int h_fail = 0;
     if (e == cudaSuccess) e = cudaMemcpy(&h_fail, fail.p, sizeof(int), cudaMemcpyDeviceToHost);

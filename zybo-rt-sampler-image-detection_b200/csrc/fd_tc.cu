@@ -1,0 +1,270 @@
+// fd_tc.cu -- MVDR steering contraction on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+//   q_f(d) = || L_f^-1 a_f(d) ||^2 ,   P(d) = sum_f 1 / q_f(d)            (see fd_mvdr.cu)
+//
+// Real formulation of the complex product y = L^-1 a, a = c + j s:
+//   [yr_i]   [ Lr_ij  -Li_ij ] [c_j]
+//   [yi_i] = [ Li_ij   Lr_ij ] [s_j]       -> one real GEMM  Y[512] = Lblk[512 x 512] * [c;s][512]
+// per (bin, direction).  MMA roles (tcgen05.mma D[M x N] += A[M x K] * B[N x K]^T, both K-major):
+//   A operand  = the phasor tile: M = 128 directions (TMEM lanes), K = (cos_j, sin_j) pairs,
+//                GENERATED on the fly by the CTA's threads (fp64 phase reduction + sincospif),
+//                never read from memory
+//   B operand  = Lblk rows: N = 256 rows per MMA (two N-tiles: rows of microphones i < 128 and
+//                i >= 128), streamed from a pre-swizzled image with 1-D bulk TMA copies
+//   D          = fp32 accumulators in TMEM: 128 lanes x 512 columns (all of TMEM)
+// so a thread (= TMEM lane = direction) ends up owning all 512 Y values of its direction and
+// q(d) is a private sum of squares: no cross-thread reduction.
+//
+// Precision: kind::tf32 with an error-compensated split x = hi + lo (hi = x with the low 13
+// mantissa bits cleared, lo = x - hi exactly): three passes A_hi*B_hi + A_hi*B_lo + A_lo*B_hi
+// (~2^-21 per product), fp32 accumulation.  "Issued" tensor flops are therefore 3x the useful
+// 8*M^2 per (bin, direction); the triangular structure of L^-1 lets N-tile 0 skip the second
+// half of K (-25 %).
+//
+// Shared-memory operand layout: K-major, 128-byte rows (32 tf32 = 16 microphones per k-chunk),
+// SWIZZLE_128B (16-byte chunk index XOR (row & 7)), 8-row groups of 1024 bytes
+// (stride_byte_offset = 1024); one k-chunk = 4 MMA k-steps of 8 (descriptor start + 32 B).
+//
+// First correct version: single-buffered (generate/copy, then MMA, then next chunk); the
+// pipelined, multicast version is the round-2 item.
+#include <math.h>
+
+#include "bf_common.cuh"
+
+namespace bf {
+
+static constexpr int kTcDirs = 128;        // directions per CTA (MMA M)
+static constexpr int kTcKc = 32;           // K elements per chunk = 16 microphones (128-byte rows)
+static constexpr int kTcMics = 256;        // this kernel is specialised for M = 256 microphones
+static constexpr int kTcRows = 2 * kTcMics;                 // 512 Lblk rows
+static constexpr int kTcChunks = 2 * kTcMics / kTcKc;       // 16 k-chunks
+static constexpr size_t kTcPlaneB = (size_t)kTcRows * 128;  // bytes of one B plane per chunk (64 KiB)
+static constexpr size_t kTcPlaneA = (size_t)kTcDirs * 128;  // bytes of one A plane per chunk (16 KiB)
+
+__device__ __forceinline__ uint32_t swz128(uint32_t off) { return off ^ (((off >> 7) & 7u) << 4); }
+
+// ---- prep: L^-1 (float2 [M][M], lower triangular) -> pre-swizzled B-operand image --------------
+// image[f][chunk][plane hi/lo][row n = 2i+part][32 k]  (k = 2*(j - 16*chunk) + {0: cos, 1: sin})
+__global__ void mvdr_tc_prep_kernel(const float2 *__restrict__ linv, unsigned char *__restrict__ image)
+{
+    const int f = blockIdx.y, chunk = blockIdx.x;
+    const float2 *L = linv + (size_t)f * kTcMics * kTcMics;
+    unsigned char *img = image + ((size_t)f * kTcChunks + chunk) * 2 * kTcPlaneB;
+    for (int e = threadIdx.x; e < kTcRows * kTcKc; e += blockDim.x) {
+        const int n = e / kTcKc, k = e - n * kTcKc;
+        const int i = n >> 1, part = n & 1;
+        const int j = chunk * (kTcKc / 2) + (k >> 1), sc = k & 1;
+        float v = 0.0f;
+        if (j <= i) {
+            const float2 l = L[(size_t)i * kTcMics + j];
+            // part 0 (yr): cos -> Lr, sin -> -Li ; part 1 (yi): cos -> Li, sin -> Lr
+            v = part == 0 ? (sc == 0 ? l.x : -l.y) : (sc == 0 ? l.y : l.x);
+        }
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const float lo = v - hi;
+        const uint32_t off = swz128((uint32_t)n * 128u + (uint32_t)k * 4u);
+        *(float *)(img + off) = hi;
+        *(float *)(img + kTcPlaneB + off) = lo;
+    }
+}
+
+// ---- tcgen05 helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
+{
+    // start address >> 4 | LBO (unused for swizzled K-major) | SBO = 1024 B | version 1 | SWIZZLE_128B
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"(bfptx::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 lanes x 32 columns (one fp32 per lane per column) -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- the kernel: grid (direction tiles, bins), 128 threads ----------------------------------------
+__global__ void __launch_bounds__(128, 1) mvdr_tc_steer_kernel(const unsigned char *__restrict__ image,
+                                                               const double *__restrict__ u, int F, int lo,
+                                                               double bin_hz, double inv_c, int D,
+                                                               float *__restrict__ qout)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    // [0, 32K): A planes (hi, lo);  [32K, 160K): B planes (hi, lo);  then barriers + tmem address
+    unsigned char *sA = smem;
+    unsigned char *sB = smem + 2 * kTcPlaneA;
+    uint64_t *bar_tma = (uint64_t *)(sB + 2 * kTcPlaneB);
+    uint64_t *bar_mma = bar_tma + 1;
+    uint32_t *tmem_slot = (uint32_t *)(bar_mma + 1);
+
+    const int t = threadIdx.x, warp = t >> 5;
+    const int f = blockIdx.y;
+    const int d = blockIdx.x * kTcDirs + t;
+    const double *ud = u + (size_t)(d < D ? d : D - 1) * kTcMics;
+    const double turns_per_u = (double)(lo + f) * bin_hz * inv_c;
+
+    if (t == 0) {
+        bfptx::mbar_init(bar_tma, 1);
+        bfptx::mbar_init(bar_mma, 1);
+        bfptx::fence_mbar_init();
+    }
+    if (warp == 0) {      // allocate all 512 TMEM columns (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;"
+                     ::"r"(bfptx::smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    // instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = 256
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+    const unsigned char *img = image + (size_t)f * kTcChunks * 2 * kTcPlaneB;
+
+    uint32_t phase = 0;
+    for (int chunk = 0; chunk < kTcChunks; chunk++) {
+        // N-tile 0 (microphone rows i < 128) only sees microphones j < 128: chunks 0..7
+        const bool tile0 = chunk < kTcChunks / 2;
+        if (chunk > 0) {                       // previous MMAs have finished reading sA / sB
+            bfptx::mbar_wait(bar_mma, phase ^ 1);
+            tc_fence_after();
+        }
+        if (t == 0) {
+            const unsigned char *src = img + (size_t)chunk * 2 * kTcPlaneB;
+            const uint32_t skip = tile0 ? 0u : (uint32_t)(kTcPlaneB / 2);        // rows 256..511 only
+            const uint32_t bytes = (uint32_t)kTcPlaneB - skip;
+            bfptx::mbar_arrive_expect_tx(bar_tma, 2 * bytes);
+            bfptx::bulk_g2s(sB + skip, src + skip, bytes, bar_tma);
+            bfptx::bulk_g2s(sB + kTcPlaneB + skip, src + kTcPlaneB + skip, bytes, bar_tma);
+        }
+        // generate the A chunk: row t = direction, 16 microphones -> (cos, sin) pairs, hi / lo planes
+        {
+            const int j0 = chunk * (kTcKc / 2);
+#pragma unroll 4
+            for (int c = 0; c < 8; c++) {                 // 16-byte chunk c holds microphones j0+2c, j0+2c+1
+                float4 hi, lo;
+                float sn, cs;
+                double turns = turns_per_u * ud[j0 + 2 * c];
+                sincospif(-2.0f * (float)(turns - rint(turns)), &sn, &cs);
+                hi.x = __uint_as_float(__float_as_uint(cs) & 0xffffe000u); lo.x = cs - hi.x;
+                hi.y = __uint_as_float(__float_as_uint(sn) & 0xffffe000u); lo.y = sn - hi.y;
+                turns = turns_per_u * ud[j0 + 2 * c + 1];
+                sincospif(-2.0f * (float)(turns - rint(turns)), &sn, &cs);
+                hi.z = __uint_as_float(__float_as_uint(cs) & 0xffffe000u); lo.z = cs - hi.z;
+                hi.w = __uint_as_float(__float_as_uint(sn) & 0xffffe000u); lo.w = sn - hi.w;
+                const uint32_t off = swz128((uint32_t)t * 128u + (uint32_t)c * 16u);
+                *(float4 *)(sA + off) = hi;
+                *(float4 *)(sA + kTcPlaneA + off) = lo;
+            }
+        }
+        bfptx::fence_proxy_async();            // generic-proxy smem writes -> visible to the async proxy
+        __syncthreads();
+        if (t == 0) {
+            bfptx::mbar_wait(bar_tma, phase);
+            tc_fence_after();
+            const uint32_t a_hi = bfptx::smem_u32(sA), a_lo = a_hi + (uint32_t)kTcPlaneA;
+            const uint32_t b_hi = bfptx::smem_u32(sB), b_lo = b_hi + (uint32_t)kTcPlaneB;
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++) {
+                if (nt == 0 && !tile0) continue;
+                const uint32_t brow = (uint32_t)nt * 256u * 128u;          // 256 rows per N-tile
+                const uint32_t dcol = tmem + (uint32_t)nt * 256u;
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {
+                    const uint32_t ko = (uint32_t)ks * 32u;                // 8 tf32 = 32 bytes per k-step
+                    const uint32_t acc = (chunk > 0 || ks > 0) ? 1u : 0u;
+                    umma_tf32(dcol, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + brow + ko), idesc, acc);
+                    umma_tf32(dcol, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_lo + brow + ko), idesc, 1u);
+                    umma_tf32(dcol, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_hi + brow + ko), idesc, 1u);
+                }
+            }
+            umma_commit(bar_mma);              // implies tcgen05.fence::before_thread_sync
+        }
+        phase ^= 1;
+    }
+    // ---- epilogue: thread t = TMEM lane t = direction: q = sum over the 512 columns of Y^2 --------
+    bfptx::mbar_wait(bar_mma, phase ^ 1);
+    tc_fence_after();
+    float q = 0.0f;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < 512; c0 += 32) {
+        float v[32];
+        tmem_ld32(lane_base + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; i++) q = fmaf(v[i], v[i], q);
+    }
+    if (d < D) qout[(size_t)f * D + d] = q;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// P[d] = sum_f 1/q[f][d]   (fixed order: deterministic)
+__global__ void mvdr_tc_reduce_kernel(const float *__restrict__ q, int F, int D, float *__restrict__ power)
+{
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    float p = 0.0f;
+    for (int f = 0; f < F; f++) p += 1.0f / q[(size_t)f * D + d];
+    power[d] = p;
+}
+
+static DevBuf g_image, g_q;
+
+int mvdr_steer_tc(const float2 *d_linv, const double *d_u, int M, int F, int lo, double bin_hz, double inv_c,
+                  int D, float *d_power, cudaStream_t st)
+{
+    if (M != kTcMics) { set_error(BF_ERR_CONFIG, "tensor-core MVDR steering is specialised for 256 microphones (got %d)", M); return BF_ERR_CONFIG; }
+    int rc = g_image.ensure((size_t)F * kTcChunks * 2 * kTcPlaneB);
+    if (rc) return rc;
+    if ((rc = g_q.ensure((size_t)F * D * sizeof(float)))) return rc;
+    mvdr_tc_prep_kernel<<<dim3(kTcChunks, F), 256, 0, st>>>(d_linv, g_image.as<unsigned char>());
+    BF_CHECK_LAUNCH();
+    const size_t smem = 2 * kTcPlaneA + 2 * kTcPlaneB + 64;
+    BF_CUDA(cudaFuncSetAttribute(mvdr_tc_steer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mvdr_tc_steer_kernel<<<dim3((D + kTcDirs - 1) / kTcDirs, F), 128, smem, st>>>(
+        g_image.as<unsigned char>(), d_u, F, lo, bin_hz, inv_c, D, g_q.as<float>());
+    BF_CHECK_LAUNCH();
+    mvdr_tc_reduce_kernel<<<(D + 255) / 256, 256, 0, st>>>(g_q.as<float>(), F, D, d_power);
+    BF_CHECK_LAUNCH();
+    count_launch(3);
+    return BF_OK;
+}
+
+}  // namespace bf

@@ -212,6 +212,58 @@ class ClockSampler:
 
 
 
+def mvdr_c4(nat, L, torch, stream, bins=512, dirs=32768, K=64):
+    """BASELINE config C4: frequency-domain MVDR, 256 mics, 1024-point FFT, bins 1..512, K = 64
+    snapshots, 256 x 128 directions.  Useful flops of the steering contraction: 8*D*M^2*F
+    (SURVEY.md 8d).  Tensor roofline = useful flops / steering-kernel time against the measured
+    dense bf16 peak; the kernel issues 2.25x that in tf32 (3-pass split, -25 % triangular skip)."""
+    import realtime_scripts.calc_r_prime as rp
+    import realtime_scripts.config as cfg
+    M, N, F = 256, 1024, bins
+    res_x, res_y = 256, dirs // 256
+    D = res_x * res_y
+    pos_all, _ = rp.calc_r_prime(cfg.ELEMENT_DISTANCE)
+    x_max = np.tan(np.deg2rad(cfg.VIEW_ANGLE / 2))
+    xs = np.linspace(-x_max, x_max, res_x)
+    ys = np.linspace(-x_max / cfg.ASPECT_RATIO, x_max / cfg.ASPECT_RATIO, res_y)
+    act = np.arange(M, dtype=np.int32)
+    p = nat.ptr
+    mx, my = np.ascontiguousarray(pos_all[0]), np.ascontiguousarray(pos_all[1])
+    nat.check(L.bf_fd_setup(M, N, 48828.0, 343.0, 1, 1 + F, p(xs), res_x, p(ys), res_y, 1.0, p(mx), p(my), p(act), M))
+    gen = torch.Generator(device="cuda").manual_seed(1237)
+    snaps = 0.05 * torch.randn((K, M, N), generator=gen, device="cuda")
+    t = torch.arange(N, device="cuda")[None, None, :]
+    m = torch.arange(M, device="cuda")[None, :, None]
+    for f0, amp, slope in ((2000.0, 0.3, 0.011), (5000.0, 0.2, -0.023), (9000.0, 0.1, 0.005)):
+        ph = 2 * np.pi * torch.rand((K, 1, 1), generator=gen, device="cuda")
+        snaps += amp * torch.sin(2 * np.pi * f0 * (t + slope * m * 48.828) / 48828.0 + ph)
+    snaps = snaps.float().contiguous()
+    power = torch.zeros(D, device="cuda")
+    times, stage = [], np.zeros(5, np.float32)
+    for r in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        nat.check(L.bf_fd_mvdr_dev(snaps.data_ptr(), power.data_ptr(), K, 1e-2, stream))
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    L.bf_fd_mvdr_timings(nat.ptr(stage))
+    ms = float(np.mean(times[1:]))
+    useful = 8.0 * D * M * M * F
+    peak_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peak_path))["bf16_tflops"]) if os.path.exists(peak_path) else 1590.0
+    ach = useful / 1e12 / (float(stage[4]) * 1e-3)
+    return {"workload": "C4: FD-MVDR, 256 mics, 1024-pt FFT, %d bins, K=%d snapshots, %d directions, loading 1e-2" % (F, K, D),
+            "maps_per_s": 1e3 / ms, "ms_per_map": ms, "finite": bool(torch.isfinite(power).all()),
+            "stage_ms": dict(zip(["fft_f64", "covariance_f64", "cholesky_f64", "tri_inverse_f64", "steering_tcgen05"],
+                                 [float(x) for x in stage])),
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                         "kernel": "mvdr_tc_steer_kernel (tcgen05 kind::tf32, 3-pass split)",
+                         "kernel_ms": float(stage[4]), "useful_flops_per_launch": useful,
+                         "issued_over_useful": 2.25, "traffic": None,
+                         "peak_source": "measured dense bf16 burst (MEASURED_PEAKS.json); tf32 peaks at half of it"}}
+
+
 def miso_c2(args, nat, L, config, directions, torch, stream, hbm_peak):
     """BASELINE config C2: MISO single-beam output, 64-mic 8x8 array, a continuous stream of
     256-sample blocks (2^16 blocks = 4.3 GB, HBM-resident, >> L2), pad and lerp delays, with the
@@ -424,7 +476,7 @@ def main():
                 "fp32_frac_of_148x128_lanes": (adds / (k_ms * 1e-3)) / fp32_peak if fp32_peak else None}
 
     # ---- e2e: the reference-facing call with host buffers -------------------------------------
-    e2e, miso = None, None
+    e2e, miso, mvdr = None, None, None
     if not args.no_extras:
         # (1) the drop-in per-buffer call: mimo_pad(signals, image, adaptive_array, n), pageable host
         #     memory, one map per call, synchronous (what PC/src/main.pyx loops do per frame)
@@ -477,6 +529,10 @@ def main():
                 miso = miso_c2(args, nat, L, config, directions, torch, stream, hbm_peak)
             except Exception as e:  # noqa: BLE001
                 miso = {"error": str(e)}
+            try:
+                mvdr = mvdr_c4(nat, L, torch, stream)
+            except Exception as e:  # noqa: BLE001
+                mvdr = {"error": str(e)}
 
     if rank == 0:
         line = {
@@ -491,7 +547,7 @@ def main():
                            world, ", one in-place NCCL all-gather per step" if world > 1 else ""),
                        "exact_sum": args.exact_sum},
             "sum_step_ms": dev_ms, "wall_s": t_wall, "gpu_launches": launches, "clocks": clocks,
-            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "miso": miso,
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "miso": miso, "mvdr": mvdr,
         }
         print(json.dumps(line))
     if world > 1:

@@ -223,8 +223,21 @@ int bf_fd_das_dev(const float *d_signals, float *d_heatmap, int frames, float th
  * 1 / Re(a^H R_f^-1 a), R_f = 1/K sum_k x_k x_k^H + loading * tr(R_f)/M * I. */
 int bf_fd_mvdr(const float *snapshots, float *power, int K, double loading);
 int bf_fd_mvdr_dev(const float *d_snapshots, float *d_power, int K, double loading, void *stream);
+/* device milliseconds of the stages of the last MVDR call: FFT, covariance + loading, Cholesky,
+ * triangular inverse, steering contraction */
+int bf_fd_mvdr_timings(float *ms5);
 /* loaded covariance of the last MVDR call: HOST double [bins][M][M][2] */
 int bf_fd_get_covariance(double *cov, size_t count);
+
+/* ---- wire-format ingest (receiver.c:94-151), SURVEY 8f "next" #1 -------------------------
+ * d_stream  device int32 [frames][n_samples][n_microphones]: the `stream` payload of
+ *           n_samples consecutive datagrams (receiver.h:51-59), header stripped
+ * d_signals device float [frames][n_microphones][n_samples] (channels >= n_arrays*rows*cols
+ *           are left untouched, like the reference's ring buffer)
+ * quirk     1 = the reference's odd-row index `row + COLUMNS - x`, 0 = corrected
+ * d_zero_mask optional uint8[n_channels]: channels to clear (api.c:835-858), or NULL */
+int bf_ingest_dev(const int *d_stream, float *d_signals, int frames, int n_arrays, int rows, int cols,
+                  double norm, int quirk, const unsigned char *d_zero_mask, void *stream);
 
 /* Counters for bench.py: kernels launched by this library since the last reset. */
 uint64_t bf_kernel_launches(int reset);

@@ -220,3 +220,37 @@ def test_host_batch_replay_equals_per_buffer_calls(algo_name, pinned):
         got = np.full((F, D), np.nan, np.float32)
         nat.check(L.bf_mimo_host_batch(algo, nat.ptr(frames), nat.ptr(got), F, nat.ptr(mics), n))
     assert bits_equal(got, single)
+
+
+@pytest.mark.parametrize("quirk", [1, 0])
+def test_wire_format_ingest_vs_oracle(quirk):
+    """datagram payloads -> [mic][sample] float buffer on the device, bit-exact
+    against the oracle's restatement of receiver.c:94-151 (with and without the reference's
+    odd-row off-by-one), plus the get_data() channel mask; then straight into the beamformer."""
+    from oracle import cpu
+    torch = _torch()
+    config, nat, L = _setup("default")
+    M, N, frames = 256, 256, 3
+    rng = np.random.default_rng(31 + quirk)
+    payload = rng.integers(-(1 << 23), 1 << 23, (frames, N, M)).astype(np.int32)
+    d_in = torch.from_numpy(payload).cuda()
+    d_out = torch.full((frames, M, N), float("nan"), device="cuda")
+    mask = np.zeros(256, np.uint8)
+    mask[[0, 1, 4, 63, 200]] = 1
+    d_mask = torch.from_numpy(mask).cuda()
+    nat.check(L.bf_ingest_dev(d_in.data_ptr(), d_out.data_ptr(), frames, 4, 8, 8, 16777216.0, quirk, None, None))
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    for f in range(frames):
+        assert bits_equal(got[f], cpu.ingest(payload[f], 4, quirk=bool(quirk)))
+    nat.check(L.bf_ingest_dev(d_in.data_ptr(), d_out.data_ptr(), frames, 4, 8, 8, 16777216.0, quirk, d_mask.data_ptr(), None))
+    torch.cuda.synchronize()
+    got2 = d_out.cpu().numpy()
+    assert not got2[:, mask == 1].any() and bits_equal(got2[:, mask == 0], got[:, mask == 0])
+    # three arrays only (ACTIVE_ARRAYS = 3 in the stock config): channels 192.. stay untouched
+    d_out3 = torch.full((1, M, N), 7.0, device="cuda")
+    nat.check(L.bf_ingest_dev(d_in.data_ptr(), d_out3.data_ptr(), 1, 3, 8, 8, 16777216.0, quirk, None, None))
+    torch.cuda.synchronize()
+    o3 = d_out3.cpu().numpy()[0]
+    assert np.all(o3[192:] == 7.0) and bits_equal(o3[:192], cpu.ingest(payload[0], 3, quirk=bool(quirk))[:192])
+    assert L.bf_ingest_dev(d_in.data_ptr(), d_out.data_ptr(), 1, 4, 8, 8, 1000.0, 1, None, None) != 0   # not 2^k

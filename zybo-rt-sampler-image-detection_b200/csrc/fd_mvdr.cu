@@ -38,6 +38,7 @@ struct MvdrState {
     int K = 0;
 };
 static MvdrState g_mv;
+static float g_stage_ms[5] = {0, 0, 0, 0, 0};     // fft, covariance+loading, cholesky, inverse, steering
 
 // ---- float64 real FFT, bins [lo,hi): same Stockham scheme as fd_rfft_kernel -----------------
 __global__ void mvdr_rfft64_kernel(const float *__restrict__ sig, const int *__restrict__ active,
@@ -232,12 +233,17 @@ int mvdr_dev(const float *d_snap, float *d_power, int K, double delta, cudaStrea
     if ((rc = work.ensure((size_t)F * M * M * sizeof(double2)))) return rc;
     if ((rc = fail.ensure(sizeof(int)))) { work.release(); return rc; }
     cudaMemsetAsync(fail.p, 0, sizeof(int), st);
+    static cudaEvent_t ev[6] = {nullptr};
+    if (!ev[0]) for (int i = 0; i < 6; i++) cudaEventCreate(&ev[i]);
+    cudaEventRecord(ev[0], st);
     const int threads = G.N / 2 < 256 ? (G.N / 2 < 32 ? 32 : G.N / 2) : 256;
     mvdr_rfft64_kernel<<<dim3(M, K), threads, 2 * G.N * sizeof(double2), st>>>(
         d_snap, G.active, M, G.n_mics, G.N, ilog2e(G.N), G.lo, G.hi, S.spec.as<double2>());
+    cudaEventRecord(ev[1], st);
     mvdr_cov_kernel<<<dim3((M + 15) / 16, (M + 15) / 16, F), dim3(16, 16), 0, st>>>(
         S.spec.as<double2>(), K, F, M, S.cov.as<double2>());
     mvdr_load_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, delta);
+    cudaEventRecord(ev[2], st);
     S.K = K;
     // keep a copy of the loaded covariance for bf_fd_get_covariance (work buffer is reused below)
     cudaError_t e = cudaGetLastError();
@@ -246,7 +252,9 @@ int mvdr_dev(const float *d_snap, float *d_power, int K, double delta, cudaStrea
     if ((rc = cov_copy.ensure((size_t)F * M * M * sizeof(double2)))) { work.release(); fail.release(); return rc; }
     cudaMemcpyAsync(cov_copy.p, S.cov.p, (size_t)F * M * M * sizeof(double2), cudaMemcpyDeviceToDevice, st);
     mvdr_chol_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, fail.as<int>());
+    cudaEventRecord(ev[3], st);
     mvdr_trinv_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, S.linv.as<float2>(), work.as<double2>());
+    cudaEventRecord(ev[4], st);
     const double bin_hz = (double)(int)((int)G.fs / 2) / (double)(G.N / 2);
     // steering contraction: tcgen05 tensor-core kernel (fd_tc.cu) for 256 microphones, CUDA-core
     // fp32 kernel otherwise (BF_MVDR_TC=0 forces the latter)
@@ -263,7 +271,9 @@ int mvdr_dev(const float *d_snap, float *d_power, int K, double delta, cudaStrea
         mvdr_steer_kernel<TD, RC><<<(G.D + TD - 1) / TD, TD, smem, st>>>(S.linv.as<float2>(), G.u, M, F, G.lo,
                                                                          bin_hz, 1.0 / G.c, G.D, d_power);
     }
+    cudaEventRecord(ev[5], st);
     e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) for (int i = 0; i < 5; i++) cudaEventElapsedTime(&g_stage_ms[i], ev[i], ev[i + 1]);
     int h_fail = 0;
     if (e == cudaSuccess) e = cudaMemcpy(&h_fail, fail.p, sizeof(int), cudaMemcpyDeviceToHost);
     // restore the covariance for inspection
@@ -306,6 +316,15 @@ int bf_fd_mvdr_dev(const float *d_snapshots, float *d_power, int K, double loadi
     if (rc) return rc;
     if (!d_snapshots || !d_power || K < 1) { set_error(BF_ERR_ARG, "bf_fd_mvdr_dev: bad arguments"); return BF_ERR_ARG; }
     return mvdr_dev(d_snapshots, d_power, K, loading, (cudaStream_t)stream);
+}
+
+// device time of each stage of the last MVDR call, milliseconds:
+// [0] float64 FFT  [1] covariance + loading  [2] Cholesky  [3] triangular inverse  [4] steering
+int bf_fd_mvdr_timings(float *ms5)
+{
+    if (!ms5) return BF_ERR_ARG;
+    for (int i = 0; i < 5; i++) ms5[i] = g_stage_ms[i];
+    return BF_OK;
 }
 
 // loaded covariance of the last bf_fd_mvdr call: HOST double [F][M][M][2] (re, im)

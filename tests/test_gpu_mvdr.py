@@ -66,9 +66,10 @@ def _oracle(snaps, g, loading):
     return R, P, Pdas
 
 
-@pytest.mark.parametrize("tensor_cores", [0, 1])
+@pytest.mark.parametrize("tensor_cores", [0, 1, 2])
 def test_mvdr_against_float64_oracle_and_das_anchor(tensor_cores, monkeypatch):
-    """tensor_cores=1: tcgen05 steering contraction (3-pass split tf32); 0: CUDA-core fp32."""
+    """tensor_cores=2: warp-specialised tcgen05 steering contraction (3-pass split tf32), 1: its
+    single-buffered first version, 0: CUDA-core fp32."""
     monkeypatch.setenv("BF_MVDR_TC", str(tensor_cores))
     g = gold("fd_das")
     bfa, nat, L = _setup()

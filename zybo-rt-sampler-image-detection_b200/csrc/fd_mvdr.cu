@@ -229,9 +229,9 @@ int mvdr_dev(const float *d_snap, float *d_power, int K, double delta, cudaStrea
     if ((rc = S.spec.ensure((size_t)K * F * M * sizeof(double2)))) return rc;
     if ((rc = S.cov.ensure((size_t)F * M * M * sizeof(double2)))) return rc;
     if ((rc = S.linv.ensure((size_t)F * M * M * sizeof(float2)))) return rc;
-    DevBuf work, fail;
+    static DevBuf work, fail;
     if ((rc = work.ensure((size_t)F * M * M * sizeof(double2)))) return rc;
-    if ((rc = fail.ensure(sizeof(int)))) { work.release(); return rc; }
+    if ((rc = fail.ensure(sizeof(int)))) return rc;
     cudaMemsetAsync(fail.p, 0, sizeof(int), st);
     static cudaEvent_t ev[6] = {nullptr};
     if (!ev[0]) for (int i = 0; i < 6; i++) cudaEventCreate(&ev[i]);
@@ -247,9 +247,9 @@ int mvdr_dev(const float *d_snap, float *d_power, int K, double delta, cudaStrea
     S.K = K;
     // keep a copy of the loaded covariance for bf_fd_get_covariance (work buffer is reused below)
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { set_error(BF_ERR_CUDA, "mvdr: %s", cudaGetErrorString(e)); work.release(); fail.release(); return BF_ERR_CUDA; }
+    if (e != cudaSuccess) { set_error(BF_ERR_CUDA, "mvdr: %s", cudaGetErrorString(e)); return BF_ERR_CUDA; }
     static DevBuf cov_copy;
-    if ((rc = cov_copy.ensure((size_t)F * M * M * sizeof(double2)))) { work.release(); fail.release(); return rc; }
+    if ((rc = cov_copy.ensure((size_t)F * M * M * sizeof(double2)))) { return rc; }
     cudaMemcpyAsync(cov_copy.p, S.cov.p, (size_t)F * M * M * sizeof(double2), cudaMemcpyDeviceToDevice, st);
     mvdr_chol_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, fail.as<int>());
     cudaEventRecord(ev[3], st);
@@ -261,8 +261,7 @@ int mvdr_dev(const float *d_snap, float *d_power, int K, double delta, cudaStrea
     const bool use_tc = M == 256 && !(getenv("BF_MVDR_TC") && atoi(getenv("BF_MVDR_TC")) == 0);
     if (use_tc) {
         if ((rc = mvdr_steer_tc(S.linv.as<float2>(), G.u, M, F, G.lo, bin_hz, 1.0 / G.c, G.D, d_power, st))) {
-            work.release(); fail.release();
-            return rc;
+                        return rc;
         }
     } else {
         constexpr int TD = 64, RC = 8;
@@ -278,8 +277,7 @@ int mvdr_dev(const float *d_snap, float *d_power, int K, double delta, cudaStrea
     if (e == cudaSuccess) e = cudaMemcpy(&h_fail, fail.p, sizeof(int), cudaMemcpyDeviceToHost);
     // restore the covariance for inspection
     cudaMemcpy(S.cov.p, cov_copy.p, (size_t)F * M * M * sizeof(double2), cudaMemcpyDeviceToDevice);
-    work.release(); fail.release();
-    count_launch(6);
+        count_launch(6);
     if (e != cudaSuccess) { set_error(BF_ERR_CUDA, "mvdr: %s", cudaGetErrorString(e)); return BF_ERR_CUDA; }
     if (h_fail) { set_error(BF_ERR_CONFIG, "mvdr: covariance not positive definite (increase loading)"); return BF_ERR_CONFIG; }
     return BF_OK;

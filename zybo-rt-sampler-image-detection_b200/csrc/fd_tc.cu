@@ -235,6 +235,184 @@ __global__ void __launch_bounds__(128, 1) mvdr_tc_steer_kernel(const unsigned ch
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+// ---- version 2: persistent, warp-specialised, double-buffered -------------------------------------
+// Roles (448 threads): warps 0-3 epilogue (TMEM lane quarters 0-3), warp 4 MMA issuer, warp 5 bulk-TMA
+// producer, warps 6-13 phasor generators (256 threads: 2 per direction).  Rings: A chunk buffers x2
+// (hi/lo planes, 32 KiB each), B slots x2 (one N-tile of one k-chunk, hi/lo planes, 64 KiB each).
+// N-tile 0 (microphone rows i < 128) finishes after chunk 7 and is read out of TMEM by the epilogue
+// warps while N-tile 1 keeps the tensor pipe busy for chunks 8..15.
+static constexpr int kV2Threads = 448;
+static constexpr size_t kV2SlotB = (size_t)256 * 128 * 2;      // one N-tile, hi + lo planes: 64 KiB
+static constexpr size_t kV2BufA = 2 * kTcPlaneA;               // hi + lo planes: 32 KiB
+
+__global__ void __launch_bounds__(kV2Threads, 1) mvdr_tc_steer_kernel2(const unsigned char *__restrict__ image,
+                                                                       const double *__restrict__ u, int F, int lo,
+                                                                       double bin_hz, double inv_c, int D, int tiles,
+                                                                       float *__restrict__ qout)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *sA = smem;                                  // 2 x 32 KiB
+    unsigned char *sB = smem + 2 * kV2BufA;                    // 2 x 64 KiB
+    uint64_t *bars = (uint64_t *)(sB + 2 * kV2SlotB);
+    uint64_t *a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 6;
+    uint64_t *t0_done = bars + 8, *acc_done = bars + 9, *acc_free = bars + 10;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 11);
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int units = F * tiles;
+
+    if (t == 0) {
+        for (int i = 0; i < 2; i++) {
+            bfptx::mbar_init(&a_full[i], 8);       // one arrive per generator warp
+            bfptx::mbar_init(&a_empty[i], 1);      // tcgen05.commit
+            bfptx::mbar_init(&b_full[i], 1);       // expect_tx arrive
+            bfptx::mbar_init(&b_empty[i], 1);      // tcgen05.commit
+        }
+        bfptx::mbar_init(t0_done, 1);
+        bfptx::mbar_init(acc_done, 1);
+        bfptx::mbar_init(acc_free, 4);             // one arrive per epilogue warp
+        bfptx::fence_mbar_init();
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;"
+                     ::"r"(bfptx::smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 5) {
+        // ================= bulk-TMA producer: B slots ==================================================
+        if (lane == 0) {
+            uint32_t k = 0;                                      // global item counter
+            for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+                const int f = unit / tiles;
+                const unsigned char *img = image + (size_t)f * kTcChunks * 2 * kTcPlaneB;
+                for (int chunk = 0; chunk < kTcChunks; chunk++) {
+                    for (int nt = (chunk < kTcChunks / 2 ? 0 : 1); nt < 2; nt++, k++) {
+                        const uint32_t slot = k & 1, ph = (k >> 1) & 1;
+                        bfptx::mbar_wait(&b_empty[slot], ph ^ 1);
+                        unsigned char *dst = sB + slot * kV2SlotB;
+                        const unsigned char *src = img + (size_t)chunk * 2 * kTcPlaneB + (size_t)nt * 256 * 128;
+                        bfptx::mbar_arrive_expect_tx(&b_full[slot], (uint32_t)kV2SlotB);
+                        bfptx::bulk_g2s(dst, src, 256 * 128, &b_full[slot]);                         // hi rows
+                        bfptx::bulk_g2s(dst + 256 * 128, src + kTcPlaneB, 256 * 128, &b_full[slot]);  // lo rows
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ================= MMA issuer =====================================================================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+            uint32_t k = 0, g = 0, w = 0;                        // item, chunk, work-unit counters
+            for (int unit = blockIdx.x; unit < units; unit += gridDim.x, w++) {
+                bfptx::mbar_wait(acc_free, (w & 1) ^ 1);          // epilogue has drained TMEM
+                tc_fence_after();
+                for (int chunk = 0; chunk < kTcChunks; chunk++, g++) {
+                    const uint32_t ab = g & 1, aph = (g >> 1) & 1;
+                    bfptx::mbar_wait(&a_full[ab], aph);
+                    const uint32_t a_hi = bfptx::smem_u32(sA + ab * kV2BufA), a_lo = a_hi + (uint32_t)kTcPlaneA;
+                    for (int nt = (chunk < kTcChunks / 2 ? 0 : 1); nt < 2; nt++, k++) {
+                        const uint32_t slot = k & 1, ph = (k >> 1) & 1;
+                        bfptx::mbar_wait(&b_full[slot], ph);
+                        tc_fence_after();
+                        const uint32_t b_hi = bfptx::smem_u32(sB + slot * kV2SlotB), b_lo = b_hi + 256u * 128u;
+                        const uint32_t dcol = tmem + (uint32_t)nt * 256u;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++) {
+                            const uint32_t ko = (uint32_t)ks * 32u;
+                            const uint32_t acc = (chunk > 0 || ks > 0) ? 1u : 0u;
+                            umma_tf32(dcol, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), idesc, acc);
+                            umma_tf32(dcol, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_lo + ko), idesc, 1u);
+                            umma_tf32(dcol, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_hi + ko), idesc, 1u);
+                        }
+                        umma_commit(&b_empty[slot]);
+                        if (nt == 0 && chunk == kTcChunks / 2 - 1) umma_commit(t0_done);
+                    }
+                    umma_commit(&a_empty[ab]);
+                }
+                umma_commit(acc_done);
+            }
+        }
+    } else if (warp >= 6) {
+        // ================= phasor generators: A chunk buffers ==========================================
+        const int gt = t - 6 * 32;                               // 0..255
+        const int row = gt & 127, half = gt >> 7;                // direction row, which 8 of the 16 microphones
+        uint32_t g = 0;
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+            const int f = unit / tiles, tile = unit - f * tiles;
+            const int d = tile * kTcDirs + row;
+            const double *ud = u + (size_t)(d < D ? d : D - 1) * kTcMics + half * 8;
+            const double turns_per_u = (double)(lo + f) * bin_hz * inv_c;
+            for (int chunk = 0; chunk < kTcChunks; chunk++, g++) {
+                const uint32_t ab = g & 1, aph = (g >> 1) & 1;
+                double uv[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) uv[i] = ud[chunk * 16 + i];
+                bfptx::mbar_wait(&a_empty[ab], aph ^ 1);
+                unsigned char *dst = sA + ab * kV2BufA;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    float4 hi, lo4;
+                    float sn, cs;
+                    double turns = turns_per_u * uv[2 * c];
+                    sincospif(-2.0f * (float)(turns - rint(turns)), &sn, &cs);
+                    hi.x = __uint_as_float(__float_as_uint(cs) & 0xffffe000u); lo4.x = cs - hi.x;
+                    hi.y = __uint_as_float(__float_as_uint(sn) & 0xffffe000u); lo4.y = sn - hi.y;
+                    turns = turns_per_u * uv[2 * c + 1];
+                    sincospif(-2.0f * (float)(turns - rint(turns)), &sn, &cs);
+                    hi.z = __uint_as_float(__float_as_uint(cs) & 0xffffe000u); lo4.z = cs - hi.z;
+                    hi.w = __uint_as_float(__float_as_uint(sn) & 0xffffe000u); lo4.w = sn - hi.w;
+                    const uint32_t off = swz128((uint32_t)row * 128u + (uint32_t)(half * 4 + c) * 16u);
+                    *(float4 *)(dst + off) = hi;
+                    *(float4 *)(dst + kTcPlaneA + off) = lo4;
+                }
+                bfptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) bfptx::mbar_arrive(&a_full[ab]);
+            }
+        }
+    } else {
+        // ================= epilogue warps 0-3: q(d) = sum over 512 columns of Y^2 ====================
+        uint32_t w = 0;
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x, w++) {
+            const int f = unit / tiles, tile = unit - f * tiles;
+            const int d = tile * kTcDirs + warp * 32 + lane;
+            float q = 0.0f;
+            bfptx::mbar_wait(t0_done, w & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < 256; c0 += 32) {
+                float v[32];
+                tmem_ld32(lane_base + (uint32_t)c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; i++) q = fmaf(v[i], v[i], q);
+            }
+            bfptx::mbar_wait(acc_done, w & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 256; c0 < 512; c0 += 32) {
+                float v[32];
+                tmem_ld32(lane_base + (uint32_t)c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; i++) q = fmaf(v[i], v[i], q);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) bfptx::mbar_arrive(acc_free);
+            if (d < D) qout[(size_t)f * D + d] = q;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 // P[d] = sum_f 1/q[f][d]   (fixed order: deterministic)
 __global__ void mvdr_tc_reduce_kernel(const float *__restrict__ q, int F, int D, float *__restrict__ power)
 {
@@ -256,10 +434,21 @@ int mvdr_steer_tc(const float2 *d_linv, const double *d_u, int M, int F, int lo,
     if ((rc = g_q.ensure((size_t)F * D * sizeof(float)))) return rc;
     mvdr_tc_prep_kernel<<<dim3(kTcChunks, F), 256, 0, st>>>(d_linv, g_image.as<unsigned char>());
     BF_CHECK_LAUNCH();
-    const size_t smem = 2 * kTcPlaneA + 2 * kTcPlaneB + 64;
-    BF_CUDA(cudaFuncSetAttribute(mvdr_tc_steer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mvdr_tc_steer_kernel<<<dim3((D + kTcDirs - 1) / kTcDirs, F), 128, smem, st>>>(
-        g_image.as<unsigned char>(), d_u, F, lo, bin_hz, inv_c, D, g_q.as<float>());
+    const int version = getenv("BF_MVDR_TC") ? atoi(getenv("BF_MVDR_TC")) : 2;
+    if (version == 1) {
+        const size_t smem = 2 * kTcPlaneA + 2 * kTcPlaneB + 64;
+        BF_CUDA(cudaFuncSetAttribute(mvdr_tc_steer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mvdr_tc_steer_kernel<<<dim3((D + kTcDirs - 1) / kTcDirs, F), 128, smem, st>>>(
+            g_image.as<unsigned char>(), d_u, F, lo, bin_hz, inv_c, D, g_q.as<float>());
+    } else {
+        const int tiles = (D + kTcDirs - 1) / kTcDirs;
+        const size_t smem = 2 * kV2BufA + 2 * kV2SlotB + 128;
+        BF_CUDA(cudaFuncSetAttribute(mvdr_tc_steer_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int units = tiles * F;
+        const int grid = units < state().sm_count ? units : state().sm_count;
+        mvdr_tc_steer_kernel2<<<grid, kV2Threads, smem, st>>>(g_image.as<unsigned char>(), d_u, F, lo, bin_hz, inv_c,
+                                                             D, tiles, g_q.as<float>());
+    }
     BF_CHECK_LAUNCH();
     mvdr_tc_reduce_kernel<<<(D + 255) / 256, 256, 0, st>>>(g_q.as<float>(), F, D, d_power);
     BF_CHECK_LAUNCH();

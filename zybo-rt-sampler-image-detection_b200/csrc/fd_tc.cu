@@ -241,14 +241,30 @@ __global__ void __launch_bounds__(128, 1) mvdr_tc_steer_kernel(const unsigned ch
 // (hi/lo planes, 32 KiB each), B slots x2 (one N-tile of one k-chunk, hi/lo planes, 64 KiB each).
 // N-tile 0 (microphone rows i < 128) finishes after chunk 7 and is read out of TMEM by the epilogue
 // warps while N-tile 1 keeps the tensor pipe busy for chunks 8..15.
-static constexpr int kV2Threads = 448;
+static constexpr int kV2GenWarps = 16;
+static constexpr int kV2Threads = (6 + kV2GenWarps) * 32;       // 704
+// k-chunks are visited in the order 0,8,1,9,...,7,15: chunks 8..15 only feed N-tile 1 (half the MMA
+// work of chunks 0..7), interleaving them evens out the MMA time per generated A chunk.
+__device__ __forceinline__ int v2_chunk(int i) { return (i & 1) ? kTcChunks / 2 + (i >> 1) : (i >> 1); }
+
+// phase table for the generators: turns per bin index, reduced: phi = tau - rint(tau),
+// tau = u * bin_hz / c, split as hi (multiple of 2^-12, so bin*hi is exact in fp32) + lo (fp32).
+__global__ void mvdr_tc_phi_kernel(const double *__restrict__ u, size_t count, double bin_hz_over_c,
+                                   float2 *__restrict__ phi)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const double tau = u[i] * bin_hz_over_c;
+    const double ph = tau - rint(tau);
+    const double hi = rint(ph * 4096.0) * (1.0 / 4096.0);
+    phi[i] = make_float2((float)hi, (float)(ph - hi));
+}
 static constexpr size_t kV2SlotB = (size_t)256 * 128 * 2;      // one N-tile, hi + lo planes: 64 KiB
 static constexpr size_t kV2BufA = 2 * kTcPlaneA;               // hi + lo planes: 32 KiB
 
 __global__ void __launch_bounds__(kV2Threads, 1) mvdr_tc_steer_kernel2(const unsigned char *__restrict__ image,
-                                                                       const double *__restrict__ u, int F, int lo,
-                                                                       double bin_hz, double inv_c, int D, int tiles,
-                                                                       float *__restrict__ qout)
+                                                                       const float2 *__restrict__ phi, int F, int lo,
+                                                                       int D, int tiles, float *__restrict__ qout)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sA = smem;                                  // 2 x 32 KiB
@@ -263,7 +279,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) mvdr_tc_steer_kernel2(const uns
 
     if (t == 0) {
         for (int i = 0; i < 2; i++) {
-            bfptx::mbar_init(&a_full[i], 8);       // one arrive per generator warp
+            bfptx::mbar_init(&a_full[i], kV2GenWarps);   // one arrive per generator warp
             bfptx::mbar_init(&a_empty[i], 1);      // tcgen05.commit
             bfptx::mbar_init(&b_full[i], 1);       // expect_tx arrive
             bfptx::mbar_init(&b_empty[i], 1);      // tcgen05.commit
@@ -290,7 +306,8 @@ __global__ void __launch_bounds__(kV2Threads, 1) mvdr_tc_steer_kernel2(const uns
             for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
                 const int f = unit / tiles;
                 const unsigned char *img = image + (size_t)f * kTcChunks * 2 * kTcPlaneB;
-                for (int chunk = 0; chunk < kTcChunks; chunk++) {
+                for (int ci = 0; ci < kTcChunks; ci++) {
+                    const int chunk = v2_chunk(ci);
                     for (int nt = (chunk < kTcChunks / 2 ? 0 : 1); nt < 2; nt++, k++) {
                         const uint32_t slot = k & 1, ph = (k >> 1) & 1;
                         bfptx::mbar_wait(&b_empty[slot], ph ^ 1);
@@ -311,7 +328,8 @@ __global__ void __launch_bounds__(kV2Threads, 1) mvdr_tc_steer_kernel2(const uns
             for (int unit = blockIdx.x; unit < units; unit += gridDim.x, w++) {
                 bfptx::mbar_wait(acc_free, (w & 1) ^ 1);          // epilogue has drained TMEM
                 tc_fence_after();
-                for (int chunk = 0; chunk < kTcChunks; chunk++, g++) {
+                for (int ci = 0; ci < kTcChunks; ci++, g++) {
+                    const int chunk = v2_chunk(ci);
                     const uint32_t ab = g & 1, aph = (g >> 1) & 1;
                     bfptx::mbar_wait(&a_full[ab], aph);
                     const uint32_t a_hi = bfptx::smem_u32(sA + ab * kV2BufA), a_lo = a_hi + (uint32_t)kTcPlaneA;
@@ -324,7 +342,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) mvdr_tc_steer_kernel2(const uns
 #pragma unroll
                         for (int ks = 0; ks < 4; ks++) {
                             const uint32_t ko = (uint32_t)ks * 32u;
-                            const uint32_t acc = (chunk > 0 || ks > 0) ? 1u : 0u;
+                            const uint32_t acc = (ci > 0 || ks > 0) ? 1u : 0u;
                             umma_tf32(dcol, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), idesc, acc);
                             umma_tf32(dcol, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_lo + ko), idesc, 1u);
                             umma_tf32(dcol, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_hi + ko), idesc, 1u);
@@ -339,36 +357,43 @@ __global__ void __launch_bounds__(kV2Threads, 1) mvdr_tc_steer_kernel2(const uns
         }
     } else if (warp >= 6) {
         // ================= phasor generators: A chunk buffers ==========================================
-        const int gt = t - 6 * 32;                               // 0..255
-        const int row = gt & 127, half = gt >> 7;                // direction row, which 8 of the 16 microphones
+        const int gt = t - 6 * 32;                               // 0..511
+        const int row = gt & 127, quarter = gt >> 7;             // direction row, which 4 of the 16 microphones
         uint32_t g = 0;
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
             const int f = unit / tiles, tile = unit - f * tiles;
             const int d = tile * kTcDirs + row;
-            const double *ud = u + (size_t)(d < D ? d : D - 1) * kTcMics + half * 8;
-            const double turns_per_u = (double)(lo + f) * bin_hz * inv_c;
-            for (int chunk = 0; chunk < kTcChunks; chunk++, g++) {
+            const float4 *pr = (const float4 *)(phi + (size_t)(d < D ? d : D - 1) * kTcMics + quarter * 4);
+            const float bin = (float)(lo + f);
+            float4 p0 = __ldg(pr + v2_chunk(0) * 8), p1 = __ldg(pr + v2_chunk(0) * 8 + 1);
+            for (int ci = 0; ci < kTcChunks; ci++, g++) {
                 const uint32_t ab = g & 1, aph = (g >> 1) & 1;
-                double uv[8];
+                const float4 c0 = p0, c1 = p1;
+                if (ci + 1 < kTcChunks) {                         // prefetch the next chunk's phases
+                    p0 = __ldg(pr + v2_chunk(ci + 1) * 8);
+                    p1 = __ldg(pr + v2_chunk(ci + 1) * 8 + 1);
+                }
+                const float ph_hi[4] = {c0.x, c0.z, c1.x, c1.z}, ph_lo[4] = {c0.y, c0.w, c1.y, c1.w};
+                float4 hi[2], lo4[2];
 #pragma unroll
-                for (int i = 0; i < 8; i++) uv[i] = ud[chunk * 16 + i];
+                for (int i = 0; i < 4; i++) {
+                    float t1 = __fmul_rn(bin, ph_hi[i]);          // exact: bin < 2^10, ph_hi multiple of 2^-12
+                    t1 = __fsub_rn(t1, rintf(t1));
+                    const float fr = __fmaf_rn(bin, ph_lo[i], t1);
+                    float sn, cs;
+                    sincospif(-2.0f * fr, &sn, &cs);
+                    const float ch = __uint_as_float(__float_as_uint(cs) & 0xffffe000u);
+                    const float sh = __uint_as_float(__float_as_uint(sn) & 0xffffe000u);
+                    if (i & 1) { hi[i >> 1].z = ch; hi[i >> 1].w = sh; lo4[i >> 1].z = cs - ch; lo4[i >> 1].w = sn - sh; }
+                    else       { hi[i >> 1].x = ch; hi[i >> 1].y = sh; lo4[i >> 1].x = cs - ch; lo4[i >> 1].y = sn - sh; }
+                }
                 bfptx::mbar_wait(&a_empty[ab], aph ^ 1);
                 unsigned char *dst = sA + ab * kV2BufA;
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    float4 hi, lo4;
-                    float sn, cs;
-                    double turns = turns_per_u * uv[2 * c];
-                    sincospif(-2.0f * (float)(turns - rint(turns)), &sn, &cs);
-                    hi.x = __uint_as_float(__float_as_uint(cs) & 0xffffe000u); lo4.x = cs - hi.x;
-                    hi.y = __uint_as_float(__float_as_uint(sn) & 0xffffe000u); lo4.y = sn - hi.y;
-                    turns = turns_per_u * uv[2 * c + 1];
-                    sincospif(-2.0f * (float)(turns - rint(turns)), &sn, &cs);
-                    hi.z = __uint_as_float(__float_as_uint(cs) & 0xffffe000u); lo4.z = cs - hi.z;
-                    hi.w = __uint_as_float(__float_as_uint(sn) & 0xffffe000u); lo4.w = sn - hi.w;
-                    const uint32_t off = swz128((uint32_t)row * 128u + (uint32_t)(half * 4 + c) * 16u);
-                    *(float4 *)(dst + off) = hi;
-                    *(float4 *)(dst + kTcPlaneA + off) = lo4;
+                for (int c = 0; c < 2; c++) {
+                    const uint32_t off = swz128((uint32_t)row * 128u + (uint32_t)(quarter * 2 + c) * 16u);
+                    *(float4 *)(dst + off) = hi[c];
+                    *(float4 *)(dst + kTcPlaneA + off) = lo4[c];
                 }
                 bfptx::fence_proxy_async();
                 __syncwarp();
@@ -446,7 +471,17 @@ int mvdr_steer_tc(const float2 *d_linv, const double *d_u, int M, int F, int lo,
         BF_CUDA(cudaFuncSetAttribute(mvdr_tc_steer_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int units = tiles * F;
         const int grid = units < state().sm_count ? units : state().sm_count;
-        mvdr_tc_steer_kernel2<<<grid, kV2Threads, smem, st>>>(g_image.as<unsigned char>(), d_u, F, lo, bin_hz, inv_c,
+        static DevBuf phi;
+        static const double *phi_key = nullptr; static int phi_D = 0; static double phi_scale = 0.0;
+        if (phi_key != d_u || phi_D != D || phi_scale != bin_hz * inv_c) {
+            const size_t cnt = (size_t)D * M;
+            if ((rc = phi.ensure(cnt * sizeof(float2)))) return rc;
+            mvdr_tc_phi_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_u, cnt, bin_hz * inv_c, phi.as<float2>());
+            BF_CHECK_LAUNCH();
+            phi_key = d_u; phi_D = D; phi_scale = bin_hz * inv_c;
+        }
+        if (lo + F > 1024) { set_error(BF_ERR_CONFIG, "tensor-core MVDR: bin index must stay below 1024"); return BF_ERR_CONFIG; }
+        mvdr_tc_steer_kernel2<<<grid, kV2Threads, smem, st>>>(g_image.as<unsigned char>(), phi.as<float2>(), F, lo,
                                                              D, tiles, g_q.as<float>());
     }
     BF_CHECK_LAUNCH();

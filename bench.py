@@ -52,6 +52,14 @@ WORKLOADS = {
 }
 
 
+def _traffic(key):
+    """Per-launch DRAM traffic (or another ncu-derived figure) recorded in profiles/traffic.json."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get(key)
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -261,6 +269,7 @@ def mvdr_c4(nat, L, torch, stream, bins=512, dirs=32768, K=64):
                          "kernel": "mvdr_tc_steer_kernel (tcgen05 kind::tf32, 3-pass split)",
                          "kernel_ms": float(stage[4]), "useful_flops_per_launch": useful,
                          "issued_over_useful": 2.25, "traffic": None,
+                         "tensor_pipe_active_pct_ncu": _traffic("mvdr_tc_steer_tensor_pipe_active_pct"),
                          "peak_source": "measured dense bf16 burst (MEASURED_PEAKS.json); tf32 peaks at half of it"}}
 
 
@@ -305,7 +314,7 @@ def miso_c2(args, nat, L, config, directions, torch, stream, hbm_peak):
                      "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                                   "frac": gbs / hbm_peak, "kernel": "miso_stream_kernel<%s>" % name,
                                   "kernel_ms": ms, "algorithmic_bytes_per_launch": blocks * blk_bytes,
-                                  "traffic": None}}
+                                  "traffic": _traffic("miso_stream_%s_%d" % (name, blocks))}}
     del sig, out
     return res
 
@@ -460,10 +469,7 @@ def main():
     launch_bytes = F * map_bytes * (d_count / D)
     hbm_peak, peak_src = peaks()
     achieved = launch_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("das_mimo_%s_F%d" % (args.algo, F))
+    traffic = _traffic("das_mimo_%s_F%d" % (args.algo, F))
     adds = F * d_count * n * N * (2 if args.algo == "lerp" else 1)
     fp32_peak = 148 * 128 * (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

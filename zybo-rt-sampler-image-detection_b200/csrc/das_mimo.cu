@@ -458,244 +458,6 @@ __global__ void __launch_bounds__((kMaxWarps + 1) * 32, 1) das_mimo_kernel(const
 }
 
 // ---------------------------------------------------------------------------
-// two-frame variant (pad, batched launches): a warp accumulates the SAME 8 directions for TWO
-// consecutive frames at once.  The table entry, its classification branch and the address
-// arithmetic are decoded once per microphone and drive 64 packed adds instead of 32, which is
-// what the single-frame kernel loses to issue overhead (ncu: fma pipe 58 % busy).  128
-// accumulator registers -> 11 consumer warps + 1 producer (384 threads, 170 registers).
-// Stage layout: per microphone [row of frame A][row of frame B], each behind P zeros.
-// ---------------------------------------------------------------------------
-static constexpr int kWarps2F = 11;
-
-template <int J, int S>
-__device__ __forceinline__ void two_run_2f(float2 (&acc0)[kR][J / 2], float2 (&acc1)[kR][J / 2],
-                                           const float2 (&a)[J / 2], const float2 (&b)[J / 2],
-                                           const float2 (&a2)[J / 2], const float2 (&b2)[J / 2])
-{
-#pragma unroll
-    for (int r = 0; r < kR; r++)
-#pragma unroll
-        for (int q = 0; q < J / 2; q++) {
-            acc0[r][q] = __fadd2_rn(acc0[r][q], r < S ? a[q] : a2[q]);
-            acc1[r][q] = __fadd2_rn(acc1[r][q], r < S ? b[q] : b2[q]);
-        }
-}
-
-// out/n, square, in-order sum over t, /N for the 8 directions of one frame (pad_and_sum.c:122-131)
-template <int J, bool EXACT>
-__device__ __forceinline__ void das_epilogue(const float2 (&acc)[kR][J / 2], float *scratch, float *img, long ds,
-                                             int valid, int lane, const MimoParams &p)
-{
-    constexpr int N = J * 32;
-    if (EXACT) {
-        float run = 0.0f;
-#pragma unroll
-        for (int q = 0; q < J / 2; q++) {
-#pragma unroll
-            for (int r = 0; r < kR; r++) {
-                float x0 = acc[r][q].x, x1 = acc[r][q].y;
-                if (p.n_pow2) { x0 = __fmul_rn(x0, p.inv_n); x1 = __fmul_rn(x1, p.inv_n); }
-                else          { x0 = __fdiv_rn(x0, p.fn);    x1 = __fdiv_rn(x1, p.fn); }
-                scratch[r * kScratchStride + lane] = __fmul_rn(x0, x0);
-                scratch[r * kScratchStride + 32 + lane] = __fmul_rn(x1, x1);
-            }
-            __syncwarp();
-            if (lane < kR) {
-                const float4 *s4 = (const float4 *)(scratch + lane * kScratchStride);
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const float4 v = s4[i];
-                    run = __fadd_rn(run, v.x);
-                    run = __fadd_rn(run, v.y);
-                    run = __fadd_rn(run, v.z);
-                    run = __fadd_rn(run, v.w);
-                }
-            }
-            __syncwarp();
-        }
-        if (lane < valid) img[lane * ds] = __fmul_rn(run, 1.0f / (float)N);
-    } else {
-        float mine = 0.0f;
-#pragma unroll
-        for (int r = 0; r < kR; r++) {
-            float t = 0.0f;
-#pragma unroll
-            for (int q = 0; q < J / 2; q++) {
-                float x0 = acc[r][q].x, x1 = acc[r][q].y;
-                if (p.n_pow2) { x0 = __fmul_rn(x0, p.inv_n); x1 = __fmul_rn(x1, p.inv_n); }
-                else          { x0 = __fdiv_rn(x0, p.fn);    x1 = __fdiv_rn(x1, p.fn); }
-                t = fmaf(x0, x0, t);
-                t = fmaf(x1, x1, t);
-            }
-#pragma unroll
-            for (int sh = 16; sh > 0; sh >>= 1) t += __shfl_xor_sync(0xffffffffu, t, sh);
-            if (lane == r) mine = t;
-        }
-        if (lane < valid) img[lane * ds] = __fmul_rn(mine, 1.0f / (float)N);
-        __syncwarp();
-    }
-}
-
-#define BF_2F_CASE(S) case S: two_run_2f<J, S>(acc0, acc1, a, b, a2, b2); break;
-
-template <int J, bool EXACT>
-__global__ void __launch_bounds__((kWarps2F + 1) * 32, 1) das_mimo2f_kernel(const MimoParams p)
-{
-    constexpr int N = J * 32;
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int W = p.W;
-    const int RS = p.P + N;
-    const size_t row_bytes = (size_t)RS * 4;
-    const size_t mic_bytes = 2 * row_bytes;              // frame A row, frame B row
-    const size_t stage_bytes = (size_t)p.Mt * mic_bytes;
-    uint64_t *full = (uint64_t *)smem;
-    uint64_t *empty = full + kStages;
-    unsigned char *stages = smem + 128;
-    float *scratch_all = (float *)(stages + kStages * stage_bytes);
-    const int pairs = (p.frames + 1) / 2;                // p.total_tiles = tiles_per_frame * pairs
-
-    {
-        const int rows_total = kStages * p.Mt * 2;
-        for (int i = threadIdx.x; i < rows_total * p.P; i += blockDim.x) {
-            int row = i / p.P, c = i - row * p.P;
-            ((float *)(stages + (size_t)row * row_bytes))[c] = 0.0f;
-        }
-        if (threadIdx.x == 0) {
-            for (int s = 0; s < kStages; s++) {
-                bfptx::mbar_init(&full[s], 1);
-                bfptx::mbar_init(&empty[s], W);
-            }
-            bfptx::fence_mbar_init();
-        }
-    }
-    __syncthreads();
-    const int nchunks = (p.n + p.Mt - 1) / p.Mt;
-    (void)pairs;
-
-    if (warp == W) {
-        int s = 0;
-        uint32_t ph = 1;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int pair = tile / p.tiles_per_frame;
-            const int fa = 2 * pair, fb = min(2 * pair + 1, p.frames - 1);
-            const float *sa = p.sig + (size_t)fa * p.n_mics_total * N;
-            const float *sb = p.sig + (size_t)fb * p.n_mics_total * N;
-            for (int c = 0; c < nchunks; c++) {
-                const int m0 = c * p.Mt;
-                const int cnt = min(p.Mt, p.n - m0);
-                bfptx::mbar_wait(&empty[s], ph);
-                if (lane == 0) bfptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(cnt * 2 * N * 4));
-                __syncwarp();
-                unsigned char *st = stages + (size_t)s * stage_bytes;
-                for (int r = lane; r < cnt; r += 32) {
-                    const int mic = p.mic_ids[m0 + r];
-                    float *dst = (float *)(st + (size_t)r * mic_bytes) + p.P;
-                    bfptx::bulk_g2s(dst, sa + (size_t)mic * N, N * 4, &full[s]);
-                    bfptx::bulk_g2s(dst + RS, sb + (size_t)mic * N, N * 4, &full[s]);
-                }
-                if (++s == kStages) { s = 0; ph ^= 1; }
-            }
-        }
-        return;
-    }
-
-    float *scratch = scratch_all + warp * (kR * kScratchStride);
-    uint4 *ebuf = (uint4 *)scratch;
-    auto group_of = [&](int tile) {
-        const int pair = tile / p.tiles_per_frame;
-        return (tile - pair * p.tiles_per_frame) * W + warp;
-    };
-    uint4 e_pref = make_uint4(kUniform, 0u, 0u, 0u);
-    auto prefetch_entries = [&](int tile, int c) {
-        if (tile >= p.total_tiles) return;
-        const int g = group_of(tile);
-        if (g >= p.groups) return;
-        const int m = min(c * p.Mt + lane, p.n - 1);
-        e_pref = __ldg(p.offs + (size_t)g * p.n + m);
-    };
-    prefetch_entries(blockIdx.x, 0);
-
-    int s = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int pair = tile / p.tiles_per_frame;
-        const int g = group_of(tile);
-        const bool active = g < p.groups;
-        float2 acc0[kR][J / 2], acc1[kR][J / 2];
-#pragma unroll
-        for (int r = 0; r < kR; r++)
-#pragma unroll
-            for (int q = 0; q < J / 2; q++) { acc0[r][q] = make_float2(0.f, 0.f); acc1[r][q] = make_float2(0.f, 0.f); }
-
-        for (int c = 0; c < nchunks; c++) {
-            const int cnt = min(p.Mt, p.n - c * p.Mt);
-            if (active) ebuf[lane] = e_pref;
-            __syncwarp();
-            if (c + 1 < nchunks) prefetch_entries(tile, c + 1);
-            else prefetch_entries(tile + gridDim.x, 0);
-            bfptx::mbar_wait(&full[s], ph);
-            if (active) {
-                const char *rowp = (const char *)(stages + (size_t)s * stage_bytes) + lane * 4;
-#pragma unroll 1
-                for (int mm = 0; mm < cnt; mm++, rowp += mic_bytes) {
-                    const uint4 e = ebuf[mm];
-                    const uint32_t kind = e.x & 3u, oa = e.x & 0xfffcu;
-                    float2 a[J / 2], b[J / 2];
-                    load_row<J>(rowp + oa, a);
-                    load_row<J>(rowp + row_bytes + oa, b);
-                    if (kind == kUniform) {
-#pragma unroll
-                        for (int r = 0; r < kR; r++)
-#pragma unroll
-                            for (int q = 0; q < J / 2; q++) {
-                                acc0[r][q] = __fadd2_rn(acc0[r][q], a[q]);
-                                acc1[r][q] = __fadd2_rn(acc1[r][q], b[q]);
-                            }
-                    } else if (kind == kTwoRun) {
-                        const uint32_t ob = e.x >> 16;
-                        float2 a2[J / 2], b2[J / 2];
-                        load_row<J>(rowp + ob, a2);
-                        load_row<J>(rowp + row_bytes + ob, b2);
-                        switch (e.y) {
-                            BF_2F_CASE(1) BF_2F_CASE(2) BF_2F_CASE(3) BF_2F_CASE(4)
-                            BF_2F_CASE(5) BF_2F_CASE(6)
-                            default: two_run_2f<J, 7>(acc0, acc1, a, b, a2, b2); break;
-                        }
-                    } else {
-                        const uint32_t ow[4] = {e.x, e.y, e.z, e.w};
-                        uint32_t prev = oa;
-#pragma unroll
-                        for (int r = 0; r < kR; r++) {
-                            const uint32_t o = (r & 1) ? (ow[r >> 1] >> 16) : (ow[r >> 1] & 0xfffcu);
-                            if (o != prev) {
-                                load_row<J>(rowp + o, a);
-                                load_row<J>(rowp + row_bytes + o, b);
-                                prev = o;
-                            }
-#pragma unroll
-                            for (int q = 0; q < J / 2; q++) {
-                                acc0[r][q] = __fadd2_rn(acc0[r][q], a[q]);
-                                acc1[r][q] = __fadd2_rn(acc1[r][q], b[q]);
-                            }
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) bfptx::mbar_arrive(&empty[s]);
-            if (++s == kStages) { s = 0; ph ^= 1; }
-        }
-        if (!active) continue;
-        const int valid = min(kR, p.d_count - g * kR);
-        const long dcol = (long)(p.d_begin + g * kR - p.d_origin) * p.img_ds;
-        das_epilogue<J, EXACT>(acc0, scratch, p.img + (long)(2 * pair) * p.img_fs + dcol, p.img_ds, valid, lane, p);
-        if (2 * pair + 1 < p.frames)
-            das_epilogue<J, EXACT>(acc1, scratch, p.img + (long)(2 * pair + 1) * p.img_fs + dcol, p.img_ds, valid, lane, p);
-    }
-}
-
-// ---------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -771,21 +533,17 @@ int mimo_tiled(int algo, const float *d_sig, float *d_img, int frames, const int
     mp.P = P;
     mp.fn = (float)n; mp.inv_n = 1.0f / (float)n; mp.n_pow2 = (n & (n - 1)) == 0;
 
-    // batched pad launches: two frames per warp (das_mimo2f_kernel) unless BF_MIMO_2F=0
-    const bool two_frames = !lerp && frames >= 2 && !(getenv("BF_MIMO_2F") && atoi(getenv("BF_MIMO_2F")) == 0);
-    const int units = two_frames ? (frames + 1) / 2 : frames;          // frame pairs or frames
-    const int wcap = two_frames ? kWarps2F : kMaxWarps;
-    const long total_groups = (long)gt->groups * units;
+    const long total_groups = (long)gt->groups * frames;
     int W = (int)((total_groups + S.sm_count - 1) / S.sm_count);
-    W = W < 1 ? 1 : (W > wcap ? wcap : W);
-    if (W > 4) W = (round_up(W + 1, 4) - 1) > wcap ? wcap : (round_up(W + 1, 4) - 1);
+    W = W < 1 ? 1 : (W > kMaxWarps ? kMaxWarps : W);
+    if (W > 4) W = (round_up(W + 1, 4) - 1) > kMaxWarps ? kMaxWarps : (round_up(W + 1, 4) - 1);
     mp.W = W;
     mp.tiles_per_frame = (gt->groups + W - 1) / W;
-    mp.total_tiles = mp.tiles_per_frame * units;
+    mp.total_tiles = mp.tiles_per_frame * frames;
     int grid = mp.total_tiles < S.sm_count ? mp.total_tiles : S.sm_count;
 
     // stage geometry: as many mic rows per stage as fit in the smem budget (<= 32: one entry per lane)
-    const size_t row_bytes = (size_t)(P + N) * 4 * ((lerp || two_frames) ? 2 : 1);
+    const size_t row_bytes = (size_t)(P + N) * 4 * (lerp ? 2 : 1);
     const size_t scratch_bytes = (size_t)W * kR * kScratchStride * 4;
     const size_t budget = 227 * 1024 - 128 - scratch_bytes - 1024;
     int Mt = 32;
@@ -803,20 +561,6 @@ int mimo_tiled(int algo, const float *d_sig, float *d_img, int frames, const int
         return BF_ERR_ARG;
     }
     const bool exact = S.exact_sum != 0;
-    if (two_frames) {
-        auto go2 = [&](auto kern) -> int {
-            BF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, (mp.W + 1) * 32, smem, st>>>(mp);
-            BF_CHECK_LAUNCH();
-            count_launch();
-            return BF_OK;
-        };
-        switch (N) {
-            case 64:  return exact ? go2(das_mimo2f_kernel<2, true>) : go2(das_mimo2f_kernel<2, false>);
-            case 128: return exact ? go2(das_mimo2f_kernel<4, true>) : go2(das_mimo2f_kernel<4, false>);
-            case 256: return exact ? go2(das_mimo2f_kernel<8, true>) : go2(das_mimo2f_kernel<8, false>);
-        }
-    }
     switch (N) {
         case 64:  return launch_J<2>(lerp, exact, mp, grid, smem, st);
         case 128: return launch_J<4>(lerp, exact, mp, grid, smem, st);

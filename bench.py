@@ -273,6 +273,37 @@ def mvdr_c4(nat, L, torch, stream, bins=512, dirs=32768, K=64):
                          "peak_source": "measured dense bf16 burst (MEASURED_PEAKS.json); tf32 peaks at half of it"}}
 
 
+def replay_c5(args, nat, torch, algo, d_mics, n, D, M, N):
+    """BASELINE config C5 on a bounded sample: a 20 s slice of a 256-channel recording resident in
+    HBM (1.0 GB, channel-major like PC/record.py's .npy), power-map video at 30 fps: window gather
+    (floor(k*fs/30)) + C3 power maps, 600 frames.  Frames are independent -> recordings / frames
+    shard over GPUs with no collective; the 1 h recording of C5 is 180 such slices."""
+    from lib import replay
+    seconds = 20
+    samples = seconds * 48828
+    gen = torch.Generator(device="cuda").manual_seed(1238)
+    rec = torch.empty((M, samples), device="cuda")
+    for i in range(0, M, 32):
+        rec[i:i + 32].normal_(generator=gen)
+    rec *= 0.05
+    total = replay.n_frames_in(samples)
+    maps = torch.empty((total, D), device="cuda")
+    replay.replay_dev(algo, rec, d_mics, n, out=maps)               # warm-up
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    replay.replay_dev(algo, rec, d_mics, n, out=maps)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    fps = total / (ms * 1e-3)
+    del rec
+    return {"workload": "C5 sample: %d s of a 256-mic recording (%.2f GB resident), 30 fps video, 180x180 maps, %d frames"
+                        % (seconds, M * samples * 4 / 1e9, total),
+            "frames_per_s": fps, "x_realtime_at_30fps": fps / 30.0, "ms": ms,
+            "one_hour_recording_s_per_gpu": 108000 / fps}
+
+
 def miso_c2(args, nat, L, config, directions, torch, stream, hbm_peak):
     """BASELINE config C2: MISO single-beam output, 64-mic 8x8 array, a continuous stream of
     256-sample blocks (2^16 blocks = 4.3 GB, HBM-resident, >> L2), pad and lerp delays, with the
@@ -482,7 +513,7 @@ def main():
                 "fp32_frac_of_148x128_lanes": (adds / (k_ms * 1e-3)) / fp32_peak if fp32_peak else None}
 
     # ---- e2e: the reference-facing call with host buffers -------------------------------------
-    e2e, miso, mvdr = None, None, None
+    e2e, miso, mvdr, replay = None, None, None, None
     if not args.no_extras:
         # (1) the drop-in per-buffer call: mimo_pad(signals, image, adaptive_array, n), pageable host
         #     memory, one map per call, synchronous (what PC/src/main.pyx loops do per frame)
@@ -529,7 +560,12 @@ def main():
                                "ms_per_map": 1e3 * float(te[1]) / single_maps}}
         del h_pool, h_maps
 
-        # ---- extra: BASELINE config C2, MISO stream (HBM-bound) ----------------------------
+        # ---- extra: BASELINE config C5 (bounded sample), then C2 and C4 -----------------------
+        if rank == 0 and args.workload == "c3":
+            try:
+                replay = replay_c5(args, nat, torch, algo, d_mics, n, D, M, N)
+            except Exception as e:  # noqa: BLE001
+                replay = {"error": str(e)}
         if rank == 0:
             try:
                 miso = miso_c2(args, nat, L, config, directions, torch, stream, hbm_peak)
@@ -553,7 +589,7 @@ def main():
                            world, ", one in-place NCCL all-gather per step" if world > 1 else ""),
                        "exact_sum": args.exact_sum},
             "sum_step_ms": dev_ms, "wall_s": t_wall, "gpu_launches": launches, "clocks": clocks,
-            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "miso": miso, "mvdr": mvdr,
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "miso": miso, "mvdr": mvdr, "replay": replay,
         }
         print(json.dumps(line))
     if world > 1:

@@ -239,6 +239,13 @@ int bf_fd_get_covariance(double *cov, size_t count);
 int bf_ingest_dev(const int *d_stream, float *d_signals, int frames, int n_arrays, int rows, int cols,
                   double norm, int quirk, const unsigned char *d_zero_mask, void *stream);
 
+/* ---- window gather for batch replay (BASELINE config C5) ---------------------------------
+ * d_recording device float [n_microphones][samples] (PC/record.py .npy layout), d_starts device
+ * int64 [frames] first sample of each frame's window; d_frames device float
+ * [frames][n_microphones][n_samples] (zero beyond the end of the recording). */
+int bf_window_dev(const float *d_recording, long samples, const long *d_starts, int frames,
+                  float *d_frames, void *stream);
+
 /* Counters for bench.py: kernels launched by this library since the last reset. */
 uint64_t bf_kernel_launches(int reset);
 

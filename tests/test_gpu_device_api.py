@@ -254,3 +254,37 @@ def test_wire_format_ingest_vs_oracle(quirk):
     o3 = d_out3.cpu().numpy()[0]
     assert np.all(o3[192:] == 7.0) and bits_equal(o3[:192], cpu.ingest(payload[0], 3, quirk=bool(quirk))[:192])
     assert L.bf_ingest_dev(d_in.data_ptr(), d_out.data_ptr(), 1, 4, 8, 8, 1000.0, 1, None, None) != 0   # not 2^k
+
+
+def test_batch_replay_windows_and_maps():
+    """BASELINE config C5 mechanics at C1 size: 30 fps windows at floor(k*fs/30) of a channel-major
+    recording -> gather kernel -> batched maps == one mimo_pad call per NumPy-sliced window."""
+    config, nat, L = _setup("c1")
+    torch = _torch()
+    from lib import directions, replay
+    g = gold("c1")
+    mics = nat.i32(g["mic_ids"])
+    D, n, N, M = 400, 64, 256, 64
+    whole, _ = directions.whole_and_f32()
+    L.load_coefficients_pad(nat.ptr(whole), whole.size)
+    nat.check()
+    starts = replay.frame_starts(5)
+    assert list(starts) == [0, 1627, 3255, 4882, 6510]          # floor(k*48828/30)
+    rng = np.random.default_rng(8)
+    rec = rng.standard_normal((M, 20000)).astype(np.float32)
+    assert replay.n_frames_in(20000) == 13
+    d_rec, d_mics = torch.from_numpy(rec).cuda(), torch.from_numpy(mics).cuda()
+    got = {}
+    for rank in range(2):                                         # frames shard over ranks, no collective
+        idx, maps = replay.replay_dev(nat.ALGO_PAD, d_rec, d_mics, n, chunk=4, rank=rank, world=2)
+        torch.cuda.synchronize()
+        for k, mp in zip(idx, maps.cpu().numpy()):
+            got[int(k)] = mp
+    assert sorted(got) == list(range(13))
+    for k in range(13):
+        s = (k * 48828) // 30
+        ref = np.zeros(D, np.float32)
+        win = np.ascontiguousarray(rec[:, s:s + N])
+        L.mimo_pad(nat.ptr(win), nat.ptr(ref), nat.ptr(mics), n)
+        nat.check()
+        assert bits_equal(got[k], ref), k

@@ -91,3 +91,36 @@ extern "C" int bf_ingest_dev(const int *d_stream, float *d_signals, int frames, 
     if (frac != 0.5) { set_error(BF_ERR_ARG, "bf_ingest_dev: NORM_FACTOR must be a power of two (got %g)", norm); return BF_ERR_ARG; }
     return ingest_dev(d_stream, d_signals, frames, n_arrays, rows, cols, norm, quirk, d_zero_mask, (cudaStream_t)stream);
 }
+
+// ---------------------------------------------------------------------------------------------
+// window gather for batch replay (BASELINE config C5): a recording is stored channel-major,
+// float [n_microphones][samples] (the .npy format of PC/record.py:28-46); every video frame k is
+// the N_SAMPLES window starting at sample starts[k] (= floor(k*fs/fps)).  Output is the frame
+// batch the beamformer kernels take: float [frames][n_microphones][n_samples].  Pure copy.
+// ---------------------------------------------------------------------------------------------
+namespace bf {
+__global__ void window_kernel(const float *__restrict__ rec, long samples, const long *__restrict__ starts,
+                              int n_mics, int N, float *__restrict__ out)
+{
+    const int f = blockIdx.y, m = blockIdx.x;
+    const long s0 = starts[f];
+    const float *src = rec + (size_t)m * samples + s0;
+    float *dst = out + ((size_t)f * n_mics + m) * N;
+    for (int t = threadIdx.x; t < N; t += blockDim.x) dst[t] = (s0 + t < samples) ? src[t] : 0.0f;
+}
+}  // namespace bf
+
+extern "C" int bf_window_dev(const float *d_recording, long samples, const long *d_starts, int frames,
+                             float *d_frames, void *stream)
+{
+    clear_error();
+    int rc = ensure_device();
+    if (rc) return rc;
+    State &S = state();
+    if (!d_recording || !d_starts || !d_frames || frames < 1 || samples < 1) { set_error(BF_ERR_ARG, "bf_window_dev: bad arguments"); return BF_ERR_ARG; }
+    const int N = S.cfg.n_samples, M = S.cfg.n_microphones;
+    bf::window_kernel<<<dim3(M, frames), N < 256 ? N : 256, 0, (cudaStream_t)stream>>>(d_recording, samples, d_starts, M, N, d_frames);
+    BF_CHECK_LAUNCH();
+    count_launch();
+    return BF_OK;
+}

@@ -65,6 +65,7 @@ def lib():
     L.bf_fd_mvdr_dev.argtypes = [vp, vp, ci, cd, vp]
     L.bf_fd_get_covariance.argtypes = [vp, cs]
     L.bf_ingest_dev.argtypes = [vp, vp, ci, ci, ci, ci, cd, ci, vp, vp]
+    L.bf_window_dev.argtypes = [vp, ctypes.c_long, vp, ci, vp, vp]
     L.bf_load_table_dev.argtypes = [ci, vp, cs]
     L.bf_generate_delays.argtypes = [ctypes.c_double, vp, ci, vp, ci, ctypes.c_double, vp, vp, ci,
                                      vp, vp, vp, ci]

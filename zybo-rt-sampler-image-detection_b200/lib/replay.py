@@ -1,0 +1,47 @@
+"""Batch replay of recordings into power-map video (BASELINE config C5).
+
+A recording is the `.npy` layout written by the reference's PC/record.py:28-46 -- float32
+(N_MICROPHONES, total_samples).  Video frame k looks at the N_SAMPLES window that starts at
+sample floor(k * fs / fps); frames are independent (the beamformer zero-pads every block, no
+history), so they shard over GPUs / ranks with no collective: rank r takes frames r, r+W, ....
+"""
+import numpy as np
+
+from interface import config
+from . import _native
+
+
+def frame_starts(n_frames, fs=48828, fps=30, first=0):
+    """floor(k*fs/fps) in integer arithmetic (hop = 1627.6 samples at 30 fps)."""
+    k = np.arange(first, first + n_frames, dtype=np.int64)
+    return (k * int(fs)) // int(fps)
+
+
+def n_frames_in(total_samples, fs=48828, fps=30):
+    """Number of complete N_SAMPLES windows available."""
+    last = total_samples - config.N_SAMPLES
+    return 0 if last < 0 else int((last * int(fps)) // int(fs)) + 1
+
+
+def replay_dev(algo, d_recording, d_mic_ids, n, fps=30, fs=48828, chunk=64, rank=0, world=1, out=None):
+    """Power maps of this rank's share of the frames of a device-resident recording.
+
+    d_recording: torch CUDA float32 (N_MICROPHONES, samples).  Returns (frame_indices, maps) with
+    maps a CUDA tensor (n_local_frames, D).  Tables must be loaded (load_coefficients_*)."""
+    import torch
+    L = _native.lib()
+    M, N = config.N_MICROPHONES, config.N_SAMPLES
+    D = config.MAX_RES_X * config.MAX_RES_Y
+    total = n_frames_in(d_recording.shape[1], fs, fps)
+    mine = np.arange(rank, total, world, dtype=np.int64)
+    starts = torch.from_numpy((mine * int(fs)) // int(fps)).cuda()
+    maps = out if out is not None else torch.empty((len(mine), D), dtype=torch.float32, device="cuda")
+    frames = torch.empty((chunk, M, N), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    for i in range(0, len(mine), chunk):
+        c = min(chunk, len(mine) - i)
+        _native.check(L.bf_window_dev(d_recording.data_ptr(), d_recording.shape[1], starts[i:].data_ptr(), c,
+                                      frames.data_ptr(), stream))
+        _native.check(L.bf_mimo_dev(algo, frames.data_ptr(), maps[i:].data_ptr(), c, d_mic_ids.data_ptr(), n,
+                                    0, D, stream))
+    return mine, maps

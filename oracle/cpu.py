@@ -159,3 +159,12 @@ def time_mimo(kind, signals, mic_ids, whole, weight, Dsub, reps):
     img = np.zeros(Dsub, np.float32)
     return lib().orc_time_mimo(int(kind), _p(signals), _p(img), _p(mic_ids), len(mic_ids), _p(whole),
                                _p(weight), int(Dsub), N, int(reps))
+
+
+def miso_hybrid(signals, mic_ids, delays_f32, offset, T):
+    signals, mic_ids = _f32(signals), _i32(mic_ids)
+    whole, taps = split_hybrid(delays_f32, T)
+    N = signals.shape[1]
+    out = np.zeros(N, np.float32)
+    lib().orc_miso_hybrid(_p(signals), _p(out), _p(mic_ids), len(mic_ids), _p(whole), _p(taps), int(offset), N, T)
+    return out

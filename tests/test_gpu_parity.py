@@ -235,3 +235,89 @@ def test_misuse_is_reported_not_undefined():
     assert L.bf_last_status() == 4                      # BF_ERR_ARG
     L.pad_mimo(nat.ptr(img), nat.ptr(mics), 16)
     assert L.bf_last_status() != 0 and b"data source" in L.bf_last_error()
+
+
+@pytest.mark.parametrize("case", ["ragged", "taps64"])
+def test_miso_fir_and_hybrid_vs_oracle(case):
+    """miso_convolve_naive / miso_convolve_vectorized / miso_convolve_hybrid:
+    single-direction FIR beams, both accumulation orders, 8 and 64 taps; offsets are in floats
+    (d*n*T) for the FIR table and in entries (d*n) for the hybrid one, as in the reference."""
+    from oracle import cpu
+    config, nat, L, g = _load_case(case)
+    from lib import directions
+    sig, mics = _signals(case, g), nat.i32(g["mic_ids"])
+    n, T, N = len(mics), config.N_TAPS, config.N_SAMPLES
+    taps = nat.f32(directions.compute_convolve_h())
+    L.load_coefficients_convolve(nat.ptr(taps), taps.size)
+    _, d32 = directions.whole_and_f32()
+    L.load_coefficients_convolve_hybrid(nat.ptr(d32), d32.size)
+    nat.check()
+    for d in (0, 7, config.MAX_RES_X * config.MAX_RES_Y - 1):
+        out = np.full(N, np.nan, np.float32)
+        L.miso_convolve_naive(nat.ptr(sig), nat.ptr(out), nat.ptr(mics), n, d * n * T)
+        nat.check()
+        assert bits_equal(out, cpu.miso_fir(sig, mics, taps, d * n * T, T, 0)), ("naive", d)
+        L.miso_convolve_vectorized(nat.ptr(sig), nat.ptr(out), nat.ptr(mics), n, d * n * T)
+        nat.check()
+        assert bits_equal(out, cpu.miso_fir(sig, mics, taps, d * n * T, T, 1)), ("vectorized", d)
+        L.miso_convolve_hybrid(nat.ptr(sig), nat.ptr(out), nat.ptr(mics), n, d * n)
+        nat.check()
+        assert bits_equal(out, cpu.miso_hybrid(sig, mics, d32, d * n, T)), ("hybrid", d)
+
+
+def test_api_h_wrappers_over_a_data_source():
+    """api.h:11-20 -- pad_mimo / lerp_mimo / convolve_mimo_* / mimo_truncated / miso_steer_listen fetch
+    the buffer from the registered source (get_data() in the reference) and then run the kernels:
+    same result as the explicit-buffer calls; load_coefficients2 feeds mimo_truncated (api.c:1004-1087)."""
+    config, nat, L, g = _load_case("ragged")
+    from lib import beamformer, directions
+    sig, mics = _signals("ragged", g), nat.i32(g["mic_ids"])
+    n, D, N = len(mics), config.MAX_RES_X * config.MAX_RES_Y, config.N_SAMPLES
+    whole, d32 = directions.whole_and_f32()
+    taps = nat.f32(directions.compute_convolve_h())
+    L.load_coefficients_pad(nat.ptr(whole), whole.size)
+    L.load_coefficients2(nat.ptr(whole), whole.size)
+    L.load_coefficients_lerp(nat.ptr(d32), d32.size)
+    L.load_coefficients_convolve(nat.ptr(taps), taps.size)
+    nat.check()
+    beamformer.connect(False, verbose=False, source=beamformer.ArraySource(sig))
+    try:
+        buf = np.empty((config.N_MICROPHONES, N), np.float32)
+        beamformer.receive(buf)
+        assert bits_equal(buf, sig)
+        for wrapper, direct in (("pad_mimo", "mimo_pad"), ("lerp_mimo", "mimo_lerp"), ("mimo_truncated", "mimo_pad"),
+                                ("convolve_mimo_naive", "mimo_convolve_naive"),
+                                ("convolve_mimo_vectorized", "mimo_convolve_vectorized")):
+            a = np.full(D, np.nan, np.float32)
+            getattr(L, wrapper)(nat.ptr(a), nat.ptr(mics), n)
+            nat.check()
+            assert bits_equal(a, _mimo(L, nat, direct, sig, mics, D)), wrapper
+        assert bits_equal(_mimo(L, nat, "mimo_pad", sig, mics, D), g["img_pad"])
+        out = np.full(N, np.nan, np.float32)
+        L.miso_steer_listen(nat.ptr(out), nat.ptr(mics), n, 38 * n)
+        nat.check()
+        assert bits_equal(out, g["miso_pad"][1])
+    finally:
+        beamformer.disconnect()
+
+
+def test_degenerate_inputs():
+    """Edge cases of the calling surface: a single direction, a single microphone, delays at and
+    beyond the block length, the largest supported block (simple kernel, N = 1024)."""
+    from oracle import cpu
+    nat = _native()
+    L = nat.lib()
+    rng = np.random.default_rng(12)
+    for N, X, Y, M, n in ((256, 1, 1, 4, 4), (1024, 3, 2, 8, 5), (32, 5, 1, 3, 1)):
+        nat.configure(M, N, 8, X, Y)
+        D = X * Y
+        sig = rng.standard_normal((M, N)).astype(np.float32)
+        mics = nat.i32(rng.permutation(M)[:n])
+        whole = rng.integers(0, N + 5, (D, n)).astype(np.int32)        # some delays beyond the block
+        d32 = (rng.random((D, n)) * (N + 3)).astype(np.float32)
+        L.load_coefficients_pad(nat.ptr(whole), whole.size)
+        L.load_coefficients_lerp(nat.ptr(d32), d32.size)
+        nat.check()
+        assert bits_equal(_mimo(L, nat, "mimo_pad", sig, mics, D), cpu.mimo_pad(sig, mics, whole, D)), (N, "pad")
+        assert bits_equal(_mimo(L, nat, "mimo_lerp", sig, mics, D), cpu.mimo_lerp(sig, mics, d32, D)), (N, "lerp")
+    nat.configure(256, 256, 8, 57, 32)

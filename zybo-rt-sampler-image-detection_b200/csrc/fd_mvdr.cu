@@ -116,11 +116,25 @@ __global__ void mvdr_chol_kernel(double2 *__restrict__ cov, int M, int *__restri
         for (int i = j + threadIdx.x; i < M; i += blockDim.x) {
             double2 s = R[(size_t)i * M + j];
             const double2 *Li = R + (size_t)i * M;
-            for (int k = 0; k < j; k++) {
-                const double2 a = Li[k], b = colj[k];     // s -= L[i][k] * conj(L[j][k])
-                s.x -= a.x * b.x + a.y * b.y;
-                s.y -= a.y * b.x - a.x * b.y;
+            // s -= sum_k L[i][k] * conj(L[j][k]); four independent partial sums (latency, not
+            // throughput, bounds this loop)
+            double px[4] = {0, 0, 0, 0}, py[4] = {0, 0, 0, 0};
+            int k = 0;
+            for (; k + 4 <= j; k += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const double2 a = Li[k + u], b = colj[k + u];
+                    px[u] += a.x * b.x + a.y * b.y;
+                    py[u] += a.y * b.x - a.x * b.y;
+                }
             }
+            for (; k < j; k++) {
+                const double2 a = Li[k], b = colj[k];
+                px[0] += a.x * b.x + a.y * b.y;
+                py[0] += a.y * b.x - a.x * b.y;
+            }
+            s.x -= (px[0] + px[1]) + (px[2] + px[3]);
+            s.y -= (py[0] + py[1]) + (py[2] + py[3]);
             if (i == j) {
                 if (!(s.x > 0.0)) { atomicExch(fail, 1); s.x = 1.0; }
                 pivot = sqrt(s.x);
@@ -150,11 +164,23 @@ __global__ void mvdr_trinv_kernel(const double2 *__restrict__ chol, int M, float
         for (int c = threadIdx.x; c < M; c += blockDim.x) {
             double2 s = make_double2(c == i ? 1.0 : 0.0, 0.0);
             if (c <= i) {
-                for (int k = c; k < i; k++) {                 // s -= L[i][k] * Z[k][c]
-                    const double2 a = L[(size_t)i * M + k], z = Z[(size_t)k * M + c];
-                    s.x -= a.x * z.x - a.y * z.y;
-                    s.y -= a.x * z.y + a.y * z.x;
+                double px[4] = {0, 0, 0, 0}, py[4] = {0, 0, 0, 0};   // s -= sum_k L[i][k] * Z[k][c]
+                int k = c;
+                for (; k + 4 <= i; k += 4) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const double2 a = L[(size_t)i * M + k + u], z = Z[(size_t)(k + u) * M + c];
+                        px[u] += a.x * z.x - a.y * z.y;
+                        py[u] += a.x * z.y + a.y * z.x;
+                    }
                 }
+                for (; k < i; k++) {
+                    const double2 a = L[(size_t)i * M + k], z = Z[(size_t)k * M + c];
+                    px[0] += a.x * z.x - a.y * z.y;
+                    py[0] += a.x * z.y + a.y * z.x;
+                }
+                s.x -= (px[0] + px[1]) + (px[2] + px[3]);
+                s.y -= (py[0] + py[1]) + (py[2] + py[3]);
                 s.x /= dii; s.y /= dii;
             } else {
                 s = make_double2(0.0, 0.0);

@@ -103,87 +103,89 @@ __global__ void mvdr_load_kernel(double2 *__restrict__ cov, int M, double delta)
     for (int i = threadIdx.x; i < M; i += blockDim.x) R[(size_t)i * M + i].x += add;
 }
 
-// ---- Cholesky R = L L^H in place (lower triangle of the row-major matrix), one CTA per bin;
-//      thread i owns row i.  Column by column (right-looking dot form). ----------------------
+// ---- Cholesky R = L L^H, one CTA per bin; thread i owns row i of L.  L is stored TRANSPOSED in
+//      the upper triangle of the row-major array (element L[i][k] lives at [k][i]) so that the
+//      inner loop over k reads consecutive addresses across threads; R's own upper triangle
+//      supplies R[i][j] = conj(R[j][i]) with the same access pattern. ------------------------------
 __global__ void mvdr_chol_kernel(double2 *__restrict__ cov, int M, int *__restrict__ fail)
 {
     double2 *R = cov + (size_t)blockIdx.x * M * M;
     __shared__ double2 colj[1024];      // L[j][0..j) of the pivot row (M <= 1024)
     __shared__ double pivot;
     for (int j = 0; j < M; j++) {
-        for (int k = threadIdx.x; k < j; k += blockDim.x) colj[k] = R[(size_t)j * M + k];
+        for (int k = threadIdx.x; k < j; k += blockDim.x) colj[k] = R[(size_t)k * M + j];
         __syncthreads();
         for (int i = j + threadIdx.x; i < M; i += blockDim.x) {
-            double2 s = R[(size_t)i * M + j];
-            const double2 *Li = R + (size_t)i * M;
-            // s -= sum_k L[i][k] * conj(L[j][k]); four independent partial sums (latency, not
-            // throughput, bounds this loop)
+            const double2 rji = R[(size_t)j * M + i];          // R[i][j] = conj(R[j][i])
+            double sx = rji.x, sy = -rji.y;
+            // s -= sum_k L[i][k] * conj(L[j][k]); four independent partial sums
             double px[4] = {0, 0, 0, 0}, py[4] = {0, 0, 0, 0};
             int k = 0;
             for (; k + 4 <= j; k += 4) {
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const double2 a = Li[k + u], b = colj[k + u];
+                    const double2 a = R[(size_t)(k + u) * M + i], b = colj[k + u];
                     px[u] += a.x * b.x + a.y * b.y;
                     py[u] += a.y * b.x - a.x * b.y;
                 }
             }
             for (; k < j; k++) {
-                const double2 a = Li[k], b = colj[k];
+                const double2 a = R[(size_t)k * M + i], b = colj[k];
                 px[0] += a.x * b.x + a.y * b.y;
                 py[0] += a.y * b.x - a.x * b.y;
             }
-            s.x -= (px[0] + px[1]) + (px[2] + px[3]);
-            s.y -= (py[0] + py[1]) + (py[2] + py[3]);
+            sx -= (px[0] + px[1]) + (px[2] + px[3]);
+            sy -= (py[0] + py[1]) + (py[2] + py[3]);
             if (i == j) {
-                if (!(s.x > 0.0)) { atomicExch(fail, 1); s.x = 1.0; }
-                pivot = sqrt(s.x);
+                if (!(sx > 0.0)) { atomicExch(fail, 1); sx = 1.0; }
+                pivot = sqrt(sx);
             }
-            R[(size_t)i * M + j] = s;                     // un-normalised; divided below
+            R[(size_t)j * M + i] = make_double2(sx, sy);       // un-normalised L[i][j] at [j][i]
         }
         __syncthreads();
         const double d = pivot;
         for (int i = j + threadIdx.x; i < M; i += blockDim.x) {
-            double2 s = R[(size_t)i * M + j];
-            R[(size_t)i * M + j] = (i == j) ? make_double2(d, 0.0) : make_double2(s.x / d, s.y / d);
+            const double2 v = R[(size_t)j * M + i];
+            R[(size_t)j * M + i] = (i == j) ? make_double2(d, 0.0) : make_double2(v.x / d, v.y / d);
         }
         __syncthreads();
     }
 }
 
-// ---- Z = L^-1 (lower triangular), forward substitution; thread c owns column c; output
-//      float2 row-major [i][c] ---------------------------------------------------------------
+// ---- Z = L^-1 (lower triangular), forward substitution row by row; thread c owns column c.
+//      L[i][k] (stored at [k][i]) is the same address for every thread of a step (broadcast),
+//      Z[k][c] is consecutive across threads.  Output float2 row-major [i][c]. --------------------
 __global__ void mvdr_trinv_kernel(const double2 *__restrict__ chol, int M, float2 *__restrict__ linv,
                                   double2 *__restrict__ work)
 {
-    const double2 *L = chol + (size_t)blockIdx.x * M * M;
+    const double2 *Lt = chol + (size_t)blockIdx.x * M * M;
     double2 *Z = work + (size_t)blockIdx.x * M * M;          // float64 copy, row-major [i][c]
     float2 *Zf = linv + (size_t)blockIdx.x * M * M;
+    __shared__ double2 rowi[1024];                           // L[i][0..i]
     for (int i = 0; i < M; i++) {
-        const double dii = L[(size_t)i * M + i].x;
+        for (int k = threadIdx.x; k <= i; k += blockDim.x) rowi[k] = Lt[(size_t)k * M + i];
+        __syncthreads();
+        const double dii = rowi[i].x;
         for (int c = threadIdx.x; c < M; c += blockDim.x) {
-            double2 s = make_double2(c == i ? 1.0 : 0.0, 0.0);
+            double2 s = make_double2(0.0, 0.0);
             if (c <= i) {
-                double px[4] = {0, 0, 0, 0}, py[4] = {0, 0, 0, 0};   // s -= sum_k L[i][k] * Z[k][c]
+                double px[2] = {c == i ? 1.0 : 0.0, 0.0}, py[2] = {0.0, 0.0};
                 int k = c;
-                for (; k + 4 <= i; k += 4) {
+                for (; k + 2 <= i; k += 2) {                   // s = delta_ic - sum_k L[i][k] * Z[k][c]
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const double2 a = L[(size_t)i * M + k + u], z = Z[(size_t)(k + u) * M + c];
-                        px[u] += a.x * z.x - a.y * z.y;
-                        py[u] += a.x * z.y + a.y * z.x;
+                    for (int u = 0; u < 2; u++) {
+                        const double2 a = rowi[k + u], z = Z[(size_t)(k + u) * M + c];
+                        px[u] -= a.x * z.x - a.y * z.y;
+                        py[u] -= a.x * z.y + a.y * z.x;
                     }
                 }
                 for (; k < i; k++) {
-                    const double2 a = L[(size_t)i * M + k], z = Z[(size_t)k * M + c];
-                    px[0] += a.x * z.x - a.y * z.y;
-                    py[0] += a.x * z.y + a.y * z.x;
+                    const double2 a = rowi[k], z = Z[(size_t)k * M + c];
+                    px[0] -= a.x * z.x - a.y * z.y;
+                    py[0] -= a.x * z.y + a.y * z.x;
                 }
-                s.x -= (px[0] + px[1]) + (px[2] + px[3]);
-                s.y -= (py[0] + py[1]) + (py[2] + py[3]);
-                s.x /= dii; s.y /= dii;
-            } else {
-                s = make_double2(0.0, 0.0);
+                s.x = (px[0] + px[1]) / dii;
+                s.y = (py[0] + py[1]) / dii;
             }
             Z[(size_t)i * M + c] = s;
             Zf[(size_t)i * M + c] = make_float2((float)s.x, (float)s.y);

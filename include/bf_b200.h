@@ -246,6 +246,56 @@ int bf_ingest_dev(const int *d_stream, float *d_signals, int frames, int n_array
 int bf_window_dev(const float *d_recording, long samples, const long *d_starts, int frames,
                   float *d_frames, void *stream);
 
+/* ---- heat-map post-processing (SURVEY 8f "next" #2) -----------------------------------------
+ * The step after the beamformer: PC/src/visual.py:130-171 calculate_heatmap (log scale),
+ * 173-205 calculate_heatmap_fft (linear), 293-322 find_power_center, 227-291
+ * calculate_heatmap_with_detection; PC/sensorfusion/decider.py:16-24 get_entropy.
+ * Maps are float [res_x][res_y] exactly as the queue payload. */
+typedef struct bf_heat_info {
+    float max_power;    /* np.max(image) */
+    float min_power;    /* np.min(np.clip(image, 1e-12, None)) */
+    float log_span;     /* np.max(img) after img -= log10(min) (log scale only) */
+    float smooth_max;   /* max of the 5x5 Gaussian-blurred map */
+    double center_col;  /* find_power_center()[0]: centroid along axis 1 (the res_y index) */
+    double center_row;  /* find_power_center()[1]: centroid along axis 0 (the res_x index) */
+    int overlay;        /* should_overlay */
+    int painted;        /* pixels at or above `amount` */
+    int fallback;       /* 1: the centroid fell back to the arg-max of the blurred map */
+    int reserved;
+} bf_heat_info;
+
+/* Fills the 256x3 colour table of generate_color_map() (visual.py:27-48): Matplotlib's jet,
+ * reversed, truncated to uint8.  Host only. */
+int bf_jet_lut(unsigned char *lut768);
+
+/* d_maps   device float [frames] maps, frame f at d_maps + f*frame_stride
+ * lut      HOST uint8[256][3] colour table, or NULL for bf_jet_lut's
+ * d_small  device uint8 [frames][res_y][res_x][3]: small_heatmap, stored flipped
+ *          (small[res_y-1-y][res_x-1-x] = lut[index]) as visual.py:166 does
+ * d_index  optional device int16 [frames][res_x][res_y]: colour index or -1 (not painted)
+ * d_info   device bf_heat_info [frames]
+ * log_scale 1 = calculate_heatmap, 0 = calculate_heatmap_fft (pass its threshold*1e6) */
+int bf_heatmap_dev(const float *d_maps, int frames, long frame_stride, int res_x, int res_y,
+                   float threshold, float amount, int exponent, int log_scale,
+                   const unsigned char *lut, unsigned char *d_small, short *d_index,
+                   bf_heat_info *d_info, void *stream);
+
+/* cv2.resize(src, (dst_w, dst_h), interpolation=cv2.INTER_LINEAR) for 8-bit images with 1..4
+ * interleaved channels, bit-identical to OpenCV 4.13; a batch of `frames` images per call. */
+int bf_resize_linear_u8_dev(const unsigned char *d_src, int frames, int src_h, int src_w, int channels,
+                            unsigned char *d_dst, int dst_h, int dst_w, void *stream);
+
+/* get_entropy (decider.py:16-24) of `frames` 8-bit images of bytes_per_frame bytes each:
+ * d_confidence[f] = 1 / (1 + H(f)). */
+int bf_entropy_dev(const unsigned char *d_img, int frames, long bytes_per_frame, double *d_confidence,
+                   void *stream);
+
+/* Host-pointer form of the whole stage: maps [frames][res_x][res_y] in; heat maps
+ * uint8 [frames][out_h][out_w][3], info [frames] and (optional) confidence [frames] out. */
+int bf_heatmap(const float *maps, int frames, int res_x, int res_y, float threshold, float amount,
+               int exponent, int log_scale, const unsigned char *lut, int out_w, int out_h,
+               unsigned char *heat_out, bf_heat_info *info_out, double *confidence_out);
+
 /* Counters for bench.py: kernels launched by this library since the last reset. */
 uint64_t bf_kernel_launches(int reset);
 

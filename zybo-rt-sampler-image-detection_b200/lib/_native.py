@@ -22,6 +22,19 @@ class BfConfig(ctypes.Structure):
                 ("fir_fused", ctypes.c_int)]
 
 
+class BfHeatInfo(ctypes.Structure):
+    _fields_ = [("max_power", ctypes.c_float), ("min_power", ctypes.c_float),
+                ("log_span", ctypes.c_float), ("smooth_max", ctypes.c_float),
+                ("center_col", ctypes.c_double), ("center_row", ctypes.c_double),
+                ("overlay", ctypes.c_int), ("painted", ctypes.c_int),
+                ("fallback", ctypes.c_int), ("reserved", ctypes.c_int)]
+
+
+HEAT_INFO_DTYPE = np.dtype([("max_power", "<f4"), ("min_power", "<f4"), ("log_span", "<f4"),
+                            ("smooth_max", "<f4"), ("center_col", "<f8"), ("center_row", "<f8"),
+                            ("overlay", "<i4"), ("painted", "<i4"), ("fallback", "<i4"),
+                            ("reserved", "<i4")])
+
 DATA_SOURCE_FN = ctypes.CFUNCTYPE(None, ctypes.POINTER(ctypes.c_float))
 
 _lib = None
@@ -66,6 +79,12 @@ def lib():
     L.bf_fd_get_covariance.argtypes = [vp, cs]
     L.bf_ingest_dev.argtypes = [vp, vp, ci, ci, ci, ci, cd, ci, vp, vp]
     L.bf_window_dev.argtypes = [vp, ctypes.c_long, vp, ci, vp, vp]
+    cf, cl = ctypes.c_float, ctypes.c_long
+    L.bf_jet_lut.argtypes = [vp]
+    L.bf_heatmap_dev.argtypes = [vp, ci, cl, ci, ci, cf, cf, ci, ci, vp, vp, vp, vp, vp]
+    L.bf_resize_linear_u8_dev.argtypes = [vp, ci, ci, ci, ci, vp, ci, ci, vp]
+    L.bf_entropy_dev.argtypes = [vp, ci, cl, vp, vp]
+    L.bf_heatmap.argtypes = [vp, ci, ci, ci, cf, cf, ci, ci, vp, ci, ci, vp, vp, vp]
     L.bf_load_table_dev.argtypes = [ci, vp, cs]
     L.bf_generate_delays.argtypes = [ctypes.c_double, vp, ci, vp, ci, ctypes.c_double, vp, vp, ci,
                                      vp, vp, vp, ci]

@@ -304,6 +304,33 @@ def replay_c5(args, nat, torch, algo, d_mics, n, D, M, N):
             "one_hour_recording_s_per_gpu": 108000 / fps}
 
 
+def heatmap_c5(torch, d_maps, hbm_peak):
+    """Post-processing of config C5's video on the device: a batch of 180x180 power maps
+    resident in HBM -> log-scale colour index + jet LUT + peak centroid (one CTA per frame), cv2-exact
+    bilinear resize to the sensor-fusion display (640x360) and to the application window (1920x1080),
+    entropy confidence.  The resize is write-bound: out bytes / time against the HBM copy peak."""
+    from lib import visual
+    frames = d_maps.shape[0]
+    out = {}
+    for (W, H) in ((640, 360), (1920, 1080)):
+        res = visual.heatmaps_dev(d_maps, window=(W, H), confidence=True)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        a.record()
+        for _ in range(reps):
+            visual.heatmaps_dev(d_maps, window=(W, H), confidence=True, out=res)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        out["%dx%d" % (W, H)] = {"frames_per_s": frames / (ms * 1e-3), "ms_per_batch": ms,
+                                 "written_GB_per_s": frames * W * H * 3 / (ms * 1e-3) / 1e9,
+                                 "frac_of_hbm_copy_peak": frames * W * H * 3 / (ms * 1e-3) / 1e9 / hbm_peak}
+        del res
+    out["workload"] = "%d maps of 180x180 (HBM-resident) -> heat overlay + peak + confidence per frame" % frames
+    return out
+
+
 def miso_c2(args, nat, L, config, directions, torch, stream, hbm_peak):
     """BASELINE config C2: MISO single-beam output, 64-mic 8x8 array, a continuous stream of
     256-sample blocks (2^16 blocks = 4.3 GB, HBM-resident, >> L2), pad and lerp delays, with the
@@ -513,7 +540,7 @@ def main():
                 "fp32_frac_of_148x128_lanes": (adds / (k_ms * 1e-3)) / fp32_peak if fp32_peak else None}
 
     # ---- e2e: the reference-facing call with host buffers -------------------------------------
-    e2e, miso, mvdr, replay = None, None, None, None
+    e2e, miso, mvdr, replay, heat = None, None, None, None, None
     if not args.no_extras:
         # (1) the drop-in per-buffer call: mimo_pad(signals, image, adaptive_array, n), pageable host
         #     memory, one map per call, synchronous (what PC/src/main.pyx loops do per frame)
@@ -566,6 +593,12 @@ def main():
                 replay = replay_c5(args, nat, torch, algo, d_mics, n, D, M, N)
             except Exception as e:  # noqa: BLE001
                 replay = {"error": str(e)}
+        if rank == 0 and args.workload == "c3":
+            try:
+                hm = d_maps if world == 1 else d_maps[:D].t().contiguous()     # [F][D] power maps of the last step
+                heat = heatmap_c5(torch, hm, hbm_peak)
+            except Exception as e:  # noqa: BLE001
+                heat = {"error": str(e)}
         if rank == 0:
             try:
                 miso = miso_c2(args, nat, L, config, directions, torch, stream, hbm_peak)
@@ -589,7 +622,7 @@ def main():
                            world, ", one in-place NCCL all-gather per step" if world > 1 else ""),
                        "exact_sum": args.exact_sum},
             "sum_step_ms": dev_ms, "wall_s": t_wall, "gpu_launches": launches, "clocks": clocks,
-            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "miso": miso, "mvdr": mvdr, "replay": replay,
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "miso": miso, "mvdr": mvdr, "replay": replay, "heatmap": heat,
         }
         print(json.dumps(line))
     if world > 1:

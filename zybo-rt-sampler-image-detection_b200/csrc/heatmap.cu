@@ -221,48 +221,58 @@ __global__ void __launch_bounds__(kHeatThreads, 1) heat_kernel(const HeatParams 
 //   fx = (float)((dx + 0.5) * scale - 0.5), sx = floor(fx), fx -= sx, clamped to the image in x
 //   (not in y: rows are clamped when fetched), coefficients = round(f * 2048) as int16,
 //   horizontal pass in int32, vertical: (((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2.
-// One thread produces 4 consecutive output bytes (one 32-bit store, coalesced).
+// A CTA row handles one SOURCE row pair (j, j+1) and every output row that interpolates between
+// them (yofs == j: dst_h/src_h rows when enlarging): a thread owns 4 consecutive output bytes,
+// does the horizontal pass for them once (8 values >> 4 kept in registers) and then only the
+// two multiplies of the vertical pass per output row; one coalesced 32-bit store per row.
 // ---------------------------------------------------------------------------------------------
-__global__ void resize_linear_u8_kernel(const unsigned char *__restrict__ src, int sh, int sw, int cn,
-                                        unsigned char *__restrict__ dst, int dh, int dw,
-                                        const int *__restrict__ xofs, const short2 *__restrict__ xco,
-                                        const int *__restrict__ yofs, const short2 *__restrict__ yco,
-                                        int aligned)
+template <int CN>
+__global__ void __launch_bounds__(256) resize_rows_kernel(const unsigned char *__restrict__ src, int sh, int sw,
+                                                          unsigned char *__restrict__ dst, int dh, int dw,
+                                                          const int *__restrict__ xofs, const short2 *__restrict__ xco,
+                                                          const short2 *__restrict__ yco, const int *__restrict__ ystart,
+                                                          int aligned)
 {
-    const int f = blockIdx.z, y = blockIdx.y;
+    const int f = blockIdx.z;
+    const int j = (int)blockIdx.y - 1;
+    const int ya = ystart[blockIdx.y], yb = ystart[blockIdx.y + 1];
+    if (ya >= yb) return;
     const int wq = blockIdx.x * blockDim.x + threadIdx.x;
-    const int row_bytes = dw * cn;
+    const int row_bytes = dw * CN;
     if (wq * 4 >= row_bytes) return;
-    const int yo = yofs[y];
-    const int y0 = yo < 0 ? 0 : (yo > sh - 1 ? sh - 1 : yo);
-    const int y1 = yo + 1 < 0 ? 0 : (yo + 1 > sh - 1 ? sh - 1 : yo + 1);
-    const short2 b = yco[y];
-    const unsigned char *r0 = src + ((size_t)f * sh + y0) * sw * cn;
-    const unsigned char *r1 = src + ((size_t)f * sh + y1) * sw * cn;
-    unsigned char *out = dst + ((size_t)f * dh + y) * row_bytes + (size_t)wq * 4;
-    unsigned int word = 0;
-    unsigned char bytes[4];
+    const int y0 = j < 0 ? 0 : (j > sh - 1 ? sh - 1 : j);
+    const int y1 = j + 1 > sh - 1 ? sh - 1 : j + 1;
+    const unsigned char *r0 = src + ((size_t)f * sh + y0) * sw * CN;
+    const unsigned char *r1 = src + ((size_t)f * sh + y1) * sw * CN;
+    int h0[4], h1[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int bi = wq * 4 + j;
-        int v = 0;
+    for (int k = 0; k < 4; k++) {
+        const int bi = wq * 4 + k;
+        h0[k] = 0; h1[k] = 0;
         if (bi < row_bytes) {
-            const int px = bi / cn, ch = bi - px * cn;
+            const int px = bi / CN, ch = bi - px * CN;
             const int sx = xofs[px];
             const int x1 = sx + 1 > sw - 1 ? sw - 1 : sx + 1;
             const short2 a = xco[px];
-            const int h0 = (int)__ldg(r0 + sx * cn + ch) * a.x + (int)__ldg(r0 + x1 * cn + ch) * a.y;
-            const int h1 = (int)__ldg(r1 + sx * cn + ch) * a.x + (int)__ldg(r1 + x1 * cn + ch) * a.y;
-            v = ((((int)b.x * (h0 >> 4)) >> 16) + (((int)b.y * (h1 >> 4)) >> 16) + 2) >> 2;
-            v = v < 0 ? 0 : (v > 255 ? 255 : v);
+            h0[k] = ((int)__ldg(r0 + sx * CN + ch) * a.x + (int)__ldg(r0 + x1 * CN + ch) * a.y) >> 4;
+            h1[k] = ((int)__ldg(r1 + sx * CN + ch) * a.x + (int)__ldg(r1 + x1 * CN + ch) * a.y) >> 4;
         }
-        bytes[j] = (unsigned char)v;
-        word |= (unsigned int)v << (8 * j);
     }
-    if (aligned && wq * 4 + 3 < row_bytes) {
-        *(unsigned int *)out = word;
-    } else {
-        for (int j = 0; j < 4 && wq * 4 + j < row_bytes; j++) out[j] = bytes[j];
+    const bool full = aligned && wq * 4 + 3 < row_bytes;
+    unsigned char *out = dst + ((size_t)f * dh + ya) * row_bytes + (size_t)wq * 4;
+    for (int y = ya; y < yb; y++, out += row_bytes) {
+        const short2 b = yco[y];
+        unsigned int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int t = ((((int)b.x * h0[k]) >> 16) + (((int)b.y * h1[k]) >> 16) + 2) >> 2;
+            v[k] = (unsigned int)(t > 255 ? 255 : t);
+        }
+        if (full) {
+            *(unsigned int *)out = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+        } else {
+            for (int k = 0; k < 4 && wq * 4 + k < row_bytes; k++) out[k] = (unsigned char)v[k];
+        }
     }
 }
 
@@ -271,48 +281,77 @@ __global__ void resize_linear_u8_kernel(const unsigned char *__restrict__ src, i
 // An 8-bit image has 256 distinct values: histogram (zeros skipped, they contribute 0), then
 // the sum over values in float64.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024, 1) entropy_kernel(const unsigned char *__restrict__ img, long bytes,
-                                                          double *__restrict__ conf)
+// A frame is split over `parts` CTAs; each adds its (non-zero-value) counts to the frame's global
+// histogram, the last one to finish (ticket counter) evaluates the sum in a fixed order and
+// clears the workspace for the next call.  Integer counts: the result does not depend on timing.
+__global__ void __launch_bounds__(512) entropy_kernel(const unsigned char *__restrict__ img, long bytes, long chunk,
+                                                      unsigned int *__restrict__ ws, double *__restrict__ conf)
 {
     __shared__ unsigned int hist[8][256];
     __shared__ double scratch[32];
-    const unsigned char *p = img + (size_t)blockIdx.x * bytes;
+    __shared__ int is_last;
+    const int f = blockIdx.y;
+    const long lo = (long)blockIdx.x * chunk;
+    const long hi = lo + chunk < bytes ? lo + chunk : bytes;
+    const unsigned char *p = img + (size_t)f * bytes;
+    unsigned int *w = ws + (size_t)f * 260;
     for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&hist[0][0])[i] = 0u;
     __syncthreads();
     unsigned int *h = hist[(threadIdx.x >> 5) & 7];
-    const bool vec = (((uintptr_t)p) & 15) == 0;
-    const long nvec = vec ? bytes / 16 : 0;
+    // 16-byte vector body between the aligned bounds, scalar head / tail
+    long va = lo + ((16 - (((uintptr_t)(p + lo)) & 15)) & 15);
+    if (va > hi) va = hi;
+    const long nvec = (hi - va) / 16;
+    for (long i = lo + threadIdx.x; i < va; i += blockDim.x) {
+        const unsigned int v = p[i];
+        if (v) atomicAdd(&h[v], 1u);
+    }
+    const uint4 *pv = (const uint4 *)(p + va);
     for (long i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const uint4 q = __ldg((const uint4 *)p + i);
-        const unsigned int w[4] = {q.x, q.y, q.z, q.w};
+        const uint4 q = __ldg(pv + i);
+        const unsigned int wd[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if (w[k] == 0u) continue;
+            if (wd[k] == 0u) continue;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const unsigned int v = (w[k] >> (8 * j)) & 255u;
+                const unsigned int v = (wd[k] >> (8 * j)) & 255u;
                 if (v) atomicAdd(&h[v], 1u);
             }
         }
     }
-    for (long i = nvec * 16 + threadIdx.x; i < bytes; i += blockDim.x) {
+    for (long i = va + nvec * 16 + threadIdx.x; i < hi; i += blockDim.x) {
         const unsigned int v = p[i];
         if (v) atomicAdd(&h[v], 1u);
     }
     __syncthreads();
+    const int v = threadIdx.x;
+    if (v > 0 && v < 256) {
+        unsigned int c = 0;
+        for (int k = 0; k < 8; k++) c += hist[k][v];
+        if (c) atomicAdd(&w[v], c);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&w[256], 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
     auto dadd_op = [](double a, double b) { return a + b; };
     double cnt = 0.0;
-    const int v = threadIdx.x;
-    if (v < 256)
-        for (int k = 0; k < 8; k++) cnt += (double)hist[k][v];
-    const double s = block_reduce(v < 256 ? cnt * (double)v : 0.0, dadd_op, 0.0, scratch);
+    if (v > 0 && v < 256) {
+        cnt = (double)__ldcg(&w[v]);
+        w[v] = 0u;
+    }
+    if (v == 0) w[256] = 0u;
+    const double s = block_reduce(cnt * (double)v, dadd_op, 0.0, scratch);
     double term = 0.0;
-    if (v > 0 && v < 256 && cnt > 0.0 && s > 0.0) {
+    if (cnt > 0.0 && s > 0.0) {
         const double pr = (double)v / s;
         term = cnt * (pr * log(pr + 1e-12));
     }
     const double ent = -block_reduce(term, dadd_op, 0.0, scratch);
-    if (threadIdx.x == 0) conf[blockIdx.x] = 1.0 / (1.0 + ent);
+    if (threadIdx.x == 0) conf[f] = 1.0 / (1.0 + ent);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -322,10 +361,11 @@ struct HeatState {
     std::mutex mu;
     DevBuf lut; bool lut_set = false;
     unsigned char lut_host[768];
-    DevBuf xofs, xco, yofs, yco;
+    DevBuf xofs, xco, yco, ystart;
     int key[4] = {-1, -1, -1, -1};
     // staging of the host-pointer entry point
     DevBuf maps, small, info, big, conf;
+    DevBuf ent_ws; int ent_frames = 0;      // [frames][260] u32, zero between calls
 };
 static HeatState &hs() { static HeatState s; return s; }
 
@@ -406,12 +446,22 @@ static int ensure_resize_tables(int sh, int sw, int dh, int dw, cudaStream_t st)
     resize_coeffs(sw, dw, true, xo, xc);
     resize_coeffs(sh, dh, false, yo, yc);
     int rc;
+    // ystart[j + 1] = first output row whose source row pair is (j, j+1), j = -1 .. sh-1 (yofs is
+    // non-decreasing and lies in [-1, sh-1]); ystart[sh + 1] = dh
+    std::vector<int> ys((size_t)sh + 2, dh);
+    for (int y = dh - 1; y >= 0; y--) {
+        int j = yo[y] < -1 ? -1 : (yo[y] > sh - 1 ? sh - 1 : yo[y]);
+        ys[(size_t)j + 1] = y;
+    }
+    for (int j = sh; j >= 0; j--)
+        if (ys[(size_t)j] > ys[(size_t)j + 1]) ys[(size_t)j] = ys[(size_t)j + 1];
+    ys[0] = 0;
     if ((rc = H.xofs.ensure(xo.size() * 4)) || (rc = H.xco.ensure(xc.size() * 2)) ||
-        (rc = H.yofs.ensure(yo.size() * 4)) || (rc = H.yco.ensure(yc.size() * 2)))
+        (rc = H.ystart.ensure(ys.size() * 4)) || (rc = H.yco.ensure(yc.size() * 2)))
         return rc;
     BF_CUDA(cudaMemcpyAsync(H.xofs.p, xo.data(), xo.size() * 4, cudaMemcpyHostToDevice, st));
     BF_CUDA(cudaMemcpyAsync(H.xco.p, xc.data(), xc.size() * 2, cudaMemcpyHostToDevice, st));
-    BF_CUDA(cudaMemcpyAsync(H.yofs.p, yo.data(), yo.size() * 4, cudaMemcpyHostToDevice, st));
+    BF_CUDA(cudaMemcpyAsync(H.ystart.p, ys.data(), ys.size() * 4, cudaMemcpyHostToDevice, st));
     BF_CUDA(cudaMemcpyAsync(H.yco.p, yc.data(), yc.size() * 2, cudaMemcpyHostToDevice, st));
     BF_CUDA(cudaStreamSynchronize(st));          // the vectors die here
     H.key[0] = sh; H.key[1] = sw; H.key[2] = dh; H.key[3] = dw;
@@ -446,7 +496,7 @@ static int heat_dev(const float *d_maps, int frames, long frame_stride, int X, i
 static int resize_dev(const unsigned char *d_src, int frames, int sh, int sw, int cn, unsigned char *d_dst, int dh,
                       int dw, cudaStream_t st)
 {
-    if (!d_src || !d_dst || frames < 1 || sh < 1 || sw < 1 || dh < 1 || dw < 1 || cn < 1 || cn > 4 || dh > 65535) {
+    if (!d_src || !d_dst || frames < 1 || sh < 1 || sw < 1 || dh < 1 || dw < 1 || cn < 1 || cn > 4 || sh > 65000) {
         set_error(BF_ERR_ARG, "bf_resize_linear_u8_dev: bad arguments");
         return BF_ERR_ARG;
     }
@@ -462,10 +512,17 @@ static int resize_dev(const unsigned char *d_src, int frames, int sh, int sw, in
     const int aligned = (row_bytes % 4 == 0) && (((uintptr_t)d_dst & 3) == 0);
     for (int f0 = 0; f0 < frames; f0 += 65535) {
         const int nf = frames - f0 < 65535 ? frames - f0 : 65535;
-        dim3 grid((words + 255) / 256, dh, nf);
-        resize_linear_u8_kernel<<<grid, 256, 0, st>>>(d_src + (size_t)f0 * sh * sw * cn, sh, sw, cn,
-                                                      d_dst + (size_t)f0 * dh * row_bytes, dh, dw, H.xofs.as<int>(),
-                                                      H.xco.as<short2>(), H.yofs.as<int>(), H.yco.as<short2>(), aligned);
+        dim3 grid((words + 255) / 256, sh + 1, nf);
+        const unsigned char *s0 = d_src + (size_t)f0 * sh * sw * cn;
+        unsigned char *o0 = d_dst + (size_t)f0 * dh * row_bytes;
+        const int *xo = H.xofs.as<int>(), *ys = H.ystart.as<int>();
+        const short2 *xc = H.xco.as<short2>(), *yc = H.yco.as<short2>();
+        switch (cn) {
+            case 1: resize_rows_kernel<1><<<grid, 256, 0, st>>>(s0, sh, sw, o0, dh, dw, xo, xc, yc, ys, aligned); break;
+            case 2: resize_rows_kernel<2><<<grid, 256, 0, st>>>(s0, sh, sw, o0, dh, dw, xo, xc, yc, ys, aligned); break;
+            case 3: resize_rows_kernel<3><<<grid, 256, 0, st>>>(s0, sh, sw, o0, dh, dw, xo, xc, yc, ys, aligned); break;
+            default: resize_rows_kernel<4><<<grid, 256, 0, st>>>(s0, sh, sw, o0, dh, dw, xo, xc, yc, ys, aligned); break;
+        }
         BF_CHECK_LAUNCH();
         count_launch();
     }
@@ -478,7 +535,23 @@ static int entropy_dev(const unsigned char *d_img, int frames, long bytes, doubl
         set_error(BF_ERR_ARG, "bf_entropy_dev: bad arguments");
         return BF_ERR_ARG;
     }
-    entropy_kernel<<<frames, 1024, 0, st>>>(d_img, bytes, d_conf);
+    HeatState &H = hs();
+    if (frames > H.ent_frames) {
+        int rc = H.ent_ws.ensure((size_t)frames * 260 * 4);
+        if (rc) return rc;
+        BF_CUDA(cudaMemsetAsync(H.ent_ws.p, 0, (size_t)frames * 260 * 4, st));
+        H.ent_frames = frames;
+    }
+    long parts = (bytes + 65535) / 65536;
+    parts = parts < 1 ? 1 : (parts > 64 ? 64 : parts);
+    long chunk = ((bytes + parts - 1) / parts + 15) / 16 * 16;
+    parts = (bytes + chunk - 1) / chunk;
+    for (int f0 = 0; f0 < frames; f0 += 65535) {
+        const int nf = frames - f0 < 65535 ? frames - f0 : 65535;
+        entropy_kernel<<<dim3((unsigned)parts, nf), 512, 0, st>>>(d_img + (size_t)f0 * bytes, bytes, chunk,
+                                                                  H.ent_ws.as<unsigned int>() + (size_t)f0 * 260,
+                                                                  d_conf + f0);
+    }
     BF_CHECK_LAUNCH();
     count_launch();
     return BF_OK;
@@ -525,6 +598,7 @@ extern "C" int bf_entropy_dev(const unsigned char *d_img, int frames, long bytes
     clear_error();
     int rc = ensure_device();
     if (rc) return rc;
+    std::lock_guard<std::mutex> lk(hs().mu);
     return entropy_dev(d_img, frames, bytes_per_frame, d_confidence, (cudaStream_t)stream);
 }
 

@@ -296,6 +296,15 @@ int bf_heatmap(const float *maps, int frames, int res_x, int res_y, float thresh
                int exponent, int log_scale, const unsigned char *lut, int out_w, int out_h,
                unsigned char *heat_out, bf_heat_info *info_out, double *confidence_out);
 
+/* ---- peak tracking filter (SURVEY 8f "next" #4), host only ----------------------------------
+ * KalmanFilter3D of PC/src/kf.hpp:36-165 (lib.kf.CyKF, kf.pyx:18-46): updatef / getStatef /
+ * predictf on an opaque handle. */
+void *bf_kf_create(void);
+void bf_kf_destroy(void *kf);
+int bf_kf_update(void *kf, const float *measurement_xyz);
+int bf_kf_get_state(void *kf, float *xyz);
+int bf_kf_predict(void *kf, int n, float *xyz);
+
 /* Counters for bench.py: kernels launched by this library since the last reset. */
 uint64_t bf_kernel_launches(int reset);
 

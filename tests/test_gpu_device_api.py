@@ -288,3 +288,40 @@ def test_batch_replay_windows_and_maps():
         L.mimo_pad(nat.ptr(win), nat.ptr(ref), nat.ptr(mics), n)
         nat.check()
         assert bits_equal(got[k], ref), k
+
+
+def test_capture_file_to_power_maps(tmp_path):
+    """a pcap of the UDP stream -> device ingest -> power maps, bit-exact against the
+    oracle chain (receiver restatement + mimo_pad) on the same datagrams."""
+    import struct
+    from oracle import cpu
+    from lib import capture, replay
+    from test_tracking_and_capture import _datagram, _udp_frame, _write_pcap
+    torch = _torch()
+    config, nat, L = _setup("default")
+    from lib import directions
+    M, N = 256, 256
+    rng = np.random.default_rng(77)
+    streams = rng.integers(-(1 << 20), 1 << 20, (2 * N + 17, M)).astype(np.int32)
+    frames = [_udp_frame(_datagram(i, s)) for i, s in enumerate(streams)]
+    path = str(tmp_path / "udp_capture.pcap")
+    _write_pcap(path, frames, 1.0 + np.arange(len(frames)) / 48828.0)
+    cap = capture.read_capture(path, n_microphones=M)
+    assert cap.dropped == 0 and cap.stream.shape == streams.shape
+    d_sig = replay.signals_from_capture(cap)
+    assert tuple(d_sig.shape) == (2, M, N)
+    mics, n = directions.active_microphones()
+    mics = nat.i32(mics)
+    whole = nat.i32(directions.calculate_delays().astype(int)).ravel()
+    L.load_coefficients_pad(nat.ptr(whole), whole.size)
+    nat.check()
+    D = config.MAX_RES_X * config.MAX_RES_Y
+    d_maps = torch.zeros((2, D), device="cuda")
+    d_mics = torch.from_numpy(mics).cuda()
+    nat.check(L.bf_mimo_dev(0, d_sig.data_ptr(), d_maps.data_ptr(), 2, d_mics.data_ptr(), n, 0, D, None))
+    torch.cuda.synchronize()
+    got_sig, got = d_sig.cpu().numpy(), d_maps.cpu().numpy()
+    for b in range(2):
+        want_sig = cpu.ingest(streams[b * N:(b + 1) * N], 4, quirk=True)
+        assert bits_equal(got_sig[b], want_sig)
+        assert bits_equal(got[b], cpu.mimo_pad(want_sig, mics, whole, D))

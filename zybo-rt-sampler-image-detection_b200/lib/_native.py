@@ -80,6 +80,12 @@ def lib():
     L.bf_ingest_dev.argtypes = [vp, vp, ci, ci, ci, ci, cd, ci, vp, vp]
     L.bf_window_dev.argtypes = [vp, ctypes.c_long, vp, ci, vp, vp]
     cf, cl = ctypes.c_float, ctypes.c_long
+    L.bf_kf_create.restype = vp
+    L.bf_kf_destroy.argtypes = [vp]
+    L.bf_kf_destroy.restype = None
+    L.bf_kf_update.argtypes = [vp, vp]
+    L.bf_kf_get_state.argtypes = [vp, vp]
+    L.bf_kf_predict.argtypes = [vp, ci, vp]
     L.bf_jet_lut.argtypes = [vp]
     L.bf_heatmap_dev.argtypes = [vp, ci, cl, ci, ci, cf, cf, ci, ci, vp, vp, vp, vp, vp]
     L.bf_resize_linear_u8_dev.argtypes = [vp, ci, ci, ci, ci, vp, ci, ci, vp]

@@ -45,3 +45,23 @@ def replay_dev(algo, d_recording, d_mic_ids, n, fps=30, fs=48828, chunk=64, rank
         _native.check(L.bf_mimo_dev(algo, frames.data_ptr(), maps[i:].data_ptr(), c, d_mic_ids.data_ptr(), n,
                                     0, D, stream))
     return mine, maps
+
+
+def signals_from_capture(cap, quirk=True, zero_mask=None, norm=16777216.0, rows=8, cols=8):
+    """Packet capture (lib.capture.read_capture) -> device sample buffers: every whole block of
+    N_SAMPLES datagrams becomes one float32 [N_MICROPHONES][N_SAMPLES] frame (the reference's receiver,
+    receiver.c:94-151, on the device).  Returns a torch CUDA tensor [blocks][N_MICROPHONES][N_SAMPLES]."""
+    import torch
+    from . import capture
+    L = _native.lib()
+    M, N = config.N_MICROPHONES, config.N_SAMPLES
+    blk = capture.blocks(cap.stream, N)
+    if blk.shape[2] != M:
+        raise ValueError("capture has %d channels per datagram, config.N_MICROPHONES is %d" % (blk.shape[2], M))
+    d_in = torch.from_numpy(np.ascontiguousarray(blk)).cuda()
+    d_out = torch.zeros((blk.shape[0], M, N), dtype=torch.float32, device="cuda")
+    d_mask = torch.from_numpy(np.ascontiguousarray(zero_mask, np.uint8)).cuda() if zero_mask is not None else None
+    _native.check(L.bf_ingest_dev(d_in.data_ptr(), d_out.data_ptr(), blk.shape[0], int(cap.n_arrays), rows, cols,
+                                  float(norm), int(bool(quirk)), d_mask.data_ptr() if d_mask is not None else None,
+                                  torch.cuda.current_stream().cuda_stream))
+    return d_out

@@ -56,6 +56,50 @@ class ShardedMaps:
                                   stream)
 
 
+class GatherPipeline:
+    """Two gather buffers and a communication stream: the all-gather of batch i runs on the comm
+    stream while the kernel of batch i+1 fills the other buffer (CUDA only).
+
+        buf = pipe.begin(i)            # waits until the gather that last used this buffer is done
+        ... launch the slice kernel into pipe.my_rows(buf) on the current stream ...
+        pipe.gather(i)                 # all-gather of buf on the comm stream, after the kernel
+        pipe.finish()                  # current stream waits for every outstanding gather
+    """
+
+    def __init__(self, n_directions, frames, rank, world, device, dist):
+        import torch
+        self.torch, self.dist = torch, dist
+        self.D, self.F, self.rank, self.world = n_directions, frames, rank, world
+        self.per, self.d_begin, self.d_count = shard_bounds(n_directions, world, rank)
+        self.bufs = [torch.zeros((self.per * world, frames), dtype=torch.float32, device=device) for _ in range(2)]
+        self.comm = torch.cuda.Stream(device=device)
+        self.done = [None, None]
+
+    def my_rows(self, buf):
+        return buf[self.rank * self.per:(self.rank + 1) * self.per]
+
+    def begin(self, i):
+        if self.done[i & 1] is not None:
+            self.torch.cuda.current_stream().wait_event(self.done[i & 1])
+        return self.bufs[i & 1]
+
+    def gather(self, i):
+        torch = self.torch
+        buf = self.bufs[i & 1]
+        ready = torch.cuda.Event()
+        ready.record()
+        self.comm.wait_event(ready)
+        with torch.cuda.stream(self.comm):
+            self.dist.all_gather_into_tensor(buf, self.my_rows(buf))
+            ev = torch.cuda.Event()
+            ev.record()
+        self.done[i & 1] = ev
+        return buf
+
+    def finish(self):
+        self.torch.cuda.current_stream().wait_stream(self.comm)
+
+
 def assemble_reference(slices, n_directions):
     """NumPy model of the gather: list of per-rank [per][F] arrays -> [D][F]."""
     return np.concatenate(slices, axis=0)[:n_directions]

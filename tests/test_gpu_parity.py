@@ -321,3 +321,53 @@ def test_degenerate_inputs():
         assert bits_equal(_mimo(L, nat, "mimo_pad", sig, mics, D), cpu.mimo_pad(sig, mics, whole, D)), (N, "pad")
         assert bits_equal(_mimo(L, nat, "mimo_lerp", sig, mics, D), cpu.mimo_lerp(sig, mics, d32, D)), (N, "lerp")
     nat.configure(256, 256, 8, 57, 32)
+
+
+@pytest.mark.parametrize("taps", [8, 16, 32])
+@pytest.mark.parametrize("n_mics,n_use", [(256, 256), (64, 37)])
+def test_fir_tiled_random_vs_oracle(taps, n_mics, n_use):
+    """Tiled FIR kernel (csrc/das_fir.cu) == one-thread-per-sample kernel == oracle, bit for bit: random
+    taps, a direction count that is not a multiple of the 8-direction group, a non-power-of-two number
+    of shuffled microphones, fused (T <= 16) and unfused (T = 32) chains, both accumulation orders, a
+    batch of frames, a direction slice written through strides, and the shuffle-tree epilogue."""
+    import torch
+    from oracle import cpu
+    nat = _native()
+    L = nat.lib()
+    X, Y, N, F = 13, 7, 256, 3
+    D = X * Y
+    nat.configure(n_mics, N, taps, X, Y)
+    rng = np.random.default_rng(taps * 100 + n_use)
+    sig = rng.standard_normal((F, n_mics, N)).astype(np.float32)
+    mics = nat.i32(rng.permutation(n_mics)[:n_use])
+    h = (rng.standard_normal((D, n_use, taps)) / taps).astype(np.float32)
+    h[5] = 0.0
+    h[6, :, 1:] = 0.0
+    L.load_coefficients_convolve(nat.ptr(h), h.size)
+    nat.check()
+    d_sig, d_mics = torch.from_numpy(sig).cuda(), torch.from_numpy(mics).cuda()
+    for algo, lanes in ((nat.ALGO_FIR_SEQ, 0), (nat.ALGO_FIR_LANES, 1)):
+        ref = np.stack([cpu.mimo_fir(sig[f], mics, h, D, taps, lanes) for f in range(F)])
+        for simple in (0, 1):
+            L.bf_set_kernel_options(simple, 1)
+            d_img = torch.full((F, D), float("nan"), device="cuda")
+            nat.check(L.bf_mimo_dev(algo, d_sig.data_ptr(), d_img.data_ptr(), F, d_mics.data_ptr(), n_use, 0, D, None))
+            torch.cuda.synchronize()
+            assert bits_equal(d_img.cpu().numpy(), ref), (algo, simple)
+        # direction slice [19, 19+40) written direction-major with origin 19
+        L.bf_set_kernel_options(0, 1)
+        d_sl = torch.full((40, F), float("nan"), device="cuda")
+        nat.check(L.bf_mimo_dev_ex(algo, d_sig.data_ptr(), d_sl.data_ptr(), F, d_mics.data_ptr(), n_use, 19, 40,
+                                   1, F, 19, None))
+        torch.cuda.synchronize()
+        assert bits_equal(np.ascontiguousarray(d_sl.cpu().numpy().T), ref[:, 19:59]), algo
+        # shuffle-tree epilogue: tolerance only
+        L.bf_set_kernel_options(0, 0)
+        d_img = torch.zeros((F, D), device="cuda")
+        nat.check(L.bf_mimo_dev(algo, d_sig.data_ptr(), d_img.data_ptr(), F, d_mics.data_ptr(), n_use, 0, D, None))
+        torch.cuda.synchronize()
+        got = d_img.cpu().numpy()
+        assert np.all(np.abs(got - ref) <= REL_TOL * np.abs(ref) + 1e-30)
+        L.bf_set_kernel_options(0, 1)
+    # the host-pointer drop-in names go through the same kernels
+    assert bits_equal(_mimo(L, nat, "mimo_convolve_naive", sig[0], mics, D), cpu.mimo_fir(sig[0], mics, h, D, taps, 0))

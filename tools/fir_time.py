@@ -26,16 +26,21 @@ L.load_coefficients_convolve(nat.ptr(taps), taps.size)
 _, d32 = directions.whole_and_f32()
 L.load_coefficients_convolve_hybrid(nat.ptr(d32), d32.size)
 nat.check()
-d_sig, d_mics = torch.from_numpy(sig[None]).cuda(), torch.from_numpy(mics).cuda()
-d_img = torch.zeros((1, D), device="cuda")
-for name, algo in (("fir_seq", nat.ALGO_FIR_SEQ), ("fir_lanes", nat.ALGO_FIR_LANES), ("hybrid", nat.ALGO_HYBRID)):
+F = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+d_sig = torch.from_numpy(np.repeat(sig[None], F, axis=0)).cuda().contiguous()
+d_mics = torch.from_numpy(mics).cuda()
+d_img = torch.zeros((F, D), device="cuda")
+for simple in (0, 1):
+  L.bf_set_kernel_options(simple, 1)
+  print("simple kernels" if simple else "tiled kernels", "(frames per launch: %d)" % F)
+  for name, algo in (("fir_seq", nat.ALGO_FIR_SEQ), ("fir_lanes", nat.ALGO_FIR_LANES), ("hybrid", nat.ALGO_HYBRID)):
     ts = []
     for i in range(6):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        nat.check(L.bf_mimo_dev(algo, d_sig.data_ptr(), d_img.data_ptr(), 1, d_mics.data_ptr(), n, 0, D, None))
+        nat.check(L.bf_mimo_dev(algo, d_sig.data_ptr(), d_img.data_ptr(), F, d_mics.data_ptr(), n, 0, D, None))
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
-    ms = float(np.mean(ts[2:]))
-    print("%-10s %.3f ms/map  %.1f maps/s  %.1f GFMA/s (D*n*N*T)" % (name, ms, 1e3 / ms, D * n * N * T / ms / 1e6))
+    ms = float(np.mean(ts[2:])) / F
+    print("  %-10s %.4f ms/map  %.1f maps/s  %.1f GFMA/s (D*n*N*T)" % (name, ms, 1e3 / ms, D * n * N * T / ms / 1e6))

@@ -195,6 +195,9 @@ static int mimo_dispatch(int algo, const float *d_sig, float *d_img, int frames,
     const bool tiled_ok = (algo == BF_ALGO_PAD || algo == BF_ALGO_LERP || algo == -1) &&
                           !S.simple_kernel && (N == 64 || N == 128 || N == 256);
     if (tiled_ok) return mimo_tiled(algo, d_sig, d_img, frames, d_mics, n, d_begin, d_count, lay, st);
+    if ((algo == BF_ALGO_FIR_SEQ || algo == BF_ALGO_FIR_LANES) && !S.simple_kernel &&
+        fir_tiled_supported(algo, N, S.cfg.n_taps))
+        return fir_tiled(algo, d_sig, d_img, frames, d_mics, n, d_begin, d_count, lay, st);
     return mimo_simple(algo, d_sig, d_img, frames, d_mics, n, d_begin, d_count, lay, st);
 }
 

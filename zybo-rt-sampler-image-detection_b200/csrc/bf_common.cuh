@@ -103,6 +103,9 @@ int launch_max_abs_i32(const int *d, size_t count, int *h_max);   // bf_tables.c
 struct ImgLayout { long frame_stride; long dir_stride; int d_origin; };
 int mimo_tiled(int algo, const float *d_sig, float *d_img, int frames, const int *d_mics, int n,
                int d_begin, int d_count, ImgLayout lay, cudaStream_t st);   // das_mimo.cu
+bool fir_tiled_supported(int algo, int N, int T);                           // das_fir.cu
+int fir_tiled(int algo, const float *d_sig, float *d_img, int frames, const int *d_mics, int n,
+              int d_begin, int d_count, ImgLayout lay, cudaStream_t st);    // das_fir.cu
 int mimo_simple(int algo, const float *d_sig, float *d_img, int frames, const int *d_mics, int n,
                 int d_begin, int d_count, ImgLayout lay, cudaStream_t st);  // das_simple.cu
 int miso_run(int algo, const float *d_sig, float *d_out, int blocks, const int *d_mics, int n,

@@ -376,6 +376,38 @@ def miso_c2(args, nat, L, config, directions, torch, stream, hbm_peak):
     del sig, out
     return res
 
+def fir_default(nat, L, config, torch, stream, clocks):
+    """FIR (fractional-delay filter) power maps at the reference's stock configuration: 57x32 grid, 256
+    mics, 256 samples, 8 taps (956 MFMA per map): mimo_convolve_naive's fused sequential
+    chain and the AVX-ordered "vectorized" variant, 16 frames per launch, tiled kernel (das_fir.cu)."""
+    config.reload(N_MICROPHONES=256, N_SAMPLES=256, MAX_RES_X=57, MAX_RES_Y=32, N_TAPS=8, SKIP_N_MICS=1,
+                  GEOMETRY_N_MICS=256, GEOMETRY_N_ARRAYS=4)
+    nat.configure_from(config)
+    D, n, N, T, F = 57 * 32, 256, 256, 8, 16
+    gen = torch.Generator(device="cuda").manual_seed(1239)
+    taps = torch.randn((D, n, T), generator=gen, device="cuda") / T       # timing does not depend on the values
+    sig = 0.1 * torch.randn((F, 256, N), generator=gen, device="cuda")
+    nat.check(L.bf_load_table_dev(nat.ALGO_FIR_SEQ, taps.data_ptr(), taps.numel()))
+    d_mics = torch.arange(n, dtype=torch.int32, device="cuda")
+    img = torch.zeros((F, D), device="cuda")
+    fp32 = 148 * 128 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+    res = {"workload": "stock config: 57x32 directions, 256 mics, 256 samples, 8 taps, %d frames per launch" % F}
+    for name, algo in (("naive_sequential", nat.ALGO_FIR_SEQ), ("vectorized_lane_order", nat.ALGO_FIR_LANES)):
+        ts = []
+        for i in range(8):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            nat.check(L.bf_mimo_dev(algo, sig.data_ptr(), img.data_ptr(), F, d_mics.data_ptr(), n, 0, D, stream))
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = float(np.mean(ts[3:]))
+        fma = F * D * n * N * T / (ms * 1e-3)
+        res[name] = {"maps_per_s": F / (ms * 1e-3), "gfma_per_s": fma / 1e9, "kernel_ms": ms,
+                     "fp32_frac_of_148x128_lanes": fma / fp32, "kernel": "das_fir_kernel"}
+    return res
+
+
 # ----------------------------------------------------------------------------------------
 # the B200 arm
 # ----------------------------------------------------------------------------------------
@@ -558,7 +590,7 @@ def main():
                 "fp32_frac_of_148x128_lanes": (adds / (k_ms * 1e-3)) / fp32_peak if fp32_peak else None}
 
     # ---- e2e: the reference-facing call with host buffers -------------------------------------
-    e2e, miso, mvdr, replay, heat = None, None, None, None, None
+    e2e, miso, mvdr, replay, heat, fir = None, None, None, None, None, None
     if not args.no_extras:
         # (1) the drop-in per-buffer call: mimo_pad(signals, image, adaptive_array, n), pageable host
         #     memory, one map per call, synchronous (what PC/src/main.pyx loops do per frame)
@@ -626,6 +658,10 @@ def main():
                 mvdr = mvdr_c4(nat, L, torch, stream)
             except Exception as e:  # noqa: BLE001
                 mvdr = {"error": str(e)}
+            try:
+                fir = fir_default(nat, L, config, torch, stream, clocks)
+            except Exception as e:  # noqa: BLE001
+                fir = {"error": str(e)}
 
     if rank == 0:
         line = {
@@ -640,7 +676,7 @@ def main():
                            world, ", one in-place NCCL all-gather per step on a second stream, overlapping the next step's kernel" if world > 1 else ""),
                        "exact_sum": args.exact_sum},
             "sum_step_ms": dev_ms, "wall_s": t_wall, "gather_check": gather_check, "gpu_launches": launches, "clocks": clocks,
-            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "miso": miso, "mvdr": mvdr, "replay": replay, "heatmap": heat,
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "miso": miso, "mvdr": mvdr, "replay": replay, "heatmap": heat, "fir": fir,
         }
         print(json.dumps(line))
     if world > 1:

@@ -297,11 +297,24 @@ def replay_c5(args, nat, torch, algo, d_mics, n, D, M, N):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
     fps = total / (ms * 1e-3)
-    del rec
+    # the same with the sensor-fusion overlay: heat map at the decider's 640x360 display size, peak and
+    # entropy confidence per frame (lib.replay.video_dev), everything device-resident
+    replay.video_dev(algo, rec, d_mics, n, keep_heat=False)
+    torch.cuda.synchronize()
+    a.record()
+    out = replay.video_dev(algo, rec, d_mics, n, keep_heat=False)
+    b.record()
+    torch.cuda.synchronize()
+    ms_v = a.elapsed_time(b)
+    conf = float(out["confidence"].mean())
+    del rec, out
     return {"workload": "C5 sample: %d s of a 256-mic recording (%.2f GB resident), 30 fps video, 180x180 maps, %d frames"
                         % (seconds, M * samples * 4 / 1e9, total),
             "frames_per_s": fps, "x_realtime_at_30fps": fps / 30.0, "ms": ms,
-            "one_hour_recording_s_per_gpu": 108000 / fps}
+            "one_hour_recording_s_per_gpu": 108000 / fps,
+            "with_overlay_640x360": {"frames_per_s": total / (ms_v * 1e-3), "ms": ms_v,
+                                     "x_realtime_at_30fps": total / (ms_v * 1e-3) / 30.0,
+                                     "mean_confidence": conf}}
 
 
 def heatmap_c5(torch, d_maps, hbm_peak):

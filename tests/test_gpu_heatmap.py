@@ -139,3 +139,33 @@ def test_entropy_and_errors():
     rc = L.bf_heatmap_dev(big.data_ptr(), 1, 300 * 300, 300, 300, 1e-7, 0.5, 5, 1, None, small.data_ptr(), None,
                           info.data_ptr(), None)
     assert rc != 0 and b"shared-memory" in L.bf_last_error()
+
+
+def test_replay_video_pipeline_matches_stagewise():
+    """lib.replay.video_dev (recording -> maps -> overlay, all on the device) == the stages run one by one."""
+    import torch
+    from lib import _native, directions, replay, visual
+    config = product_config("c1")
+    _native.configure_from(config)
+    L = _native.lib()
+    M, N = config.N_MICROPHONES, config.N_SAMPLES
+    mics, n = directions.active_microphones()
+    mics = _native.i32(mics)
+    whole = _native.i32(directions.calculate_delays().astype(int)).ravel()
+    L.load_coefficients_pad(_native.ptr(whole), whole.size)
+    _native.check()
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    rec = 0.05 * torch.randn((M, 48828 // 2), generator=gen, device="cuda")
+    rec[:, 3000:9000] += 0.2 * torch.sin(torch.arange(6000, device="cuda") * 0.6)[None, :]
+    d_mics = torch.from_numpy(mics).cuda()
+    out = replay.video_dev(_native.ALGO_PAD, rec, d_mics, n, window=(64, 36), chunk=5)
+    idx, maps = replay.replay_dev(_native.ALGO_PAD, rec, d_mics, n)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["frames"], idx) and torch.equal(out["maps"], maps) and len(idx) == 15
+    ref = visual.heatmaps_dev(maps, window=(64, 36), confidence=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out["heat"], ref["heat"]) and torch.equal(out["info"], ref["info"])
+    assert torch.equal(out["confidence"], ref["confidence"])
+    info = out["info"].cpu().numpy().view(_native.HEAT_INFO_DTYPE).ravel()
+    assert info["overlay"].all() and np.all(info["max_power"] > 0)
+    product_config("default")

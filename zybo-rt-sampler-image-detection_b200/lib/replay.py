@@ -47,6 +47,29 @@ def replay_dev(algo, d_recording, d_mic_ids, n, fps=30, fs=48828, chunk=64, rank
     return mine, maps
 
 
+def video_dev(algo, d_recording, d_mic_ids, n, window=(640, 360), fps=30, fs=48828, chunk=64, rank=0, world=1,
+              keep_heat=True, **heat_kw):
+    """BASELINE config C5 end to end on the device: recording -> 30 fps power maps -> heat overlay
+    (lib.visual.heatmaps_dev: colour map at `window` size, peak, entropy confidence) for this rank's share
+    of the frames.  Returns dict(frames=indices, maps=[k][D], info=[k][48] u8, confidence=[k],
+    heat=[k][H][W][3] u8 or None).  Nothing leaves the GPU; frames shard over ranks with no collective."""
+    import torch
+    from . import visual
+    mine, maps = replay_dev(algo, d_recording, d_mic_ids, n, fps=fps, fs=fs, chunk=chunk, rank=rank, world=world)
+    k = len(mine)
+    W, H = window
+    info = torch.empty((k, _native.HEAT_INFO_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+    conf = torch.empty(k, dtype=torch.float64, device="cuda")
+    heat = torch.empty((k if keep_heat else min(k, chunk), H, W, 3), dtype=torch.uint8, device="cuda")
+    for i in range(0, k, chunk):
+        c = min(chunk, k - i)
+        res = visual.heatmaps_dev(maps[i:i + c], window=window, confidence=True, **heat_kw)
+        info[i:i + c] = res["info"]
+        conf[i:i + c] = res["confidence"]
+        (heat[i:i + c] if keep_heat else heat[:c]).copy_(res["heat"])
+    return {"frames": mine, "maps": maps, "info": info, "confidence": conf, "heat": heat if keep_heat else None}
+
+
 def signals_from_capture(cap, quirk=True, zero_mask=None, norm=16777216.0, rows=8, cols=8):
     """Packet capture (lib.capture.read_capture) -> device sample buffers: every whole block of
     N_SAMPLES datagrams becomes one float32 [N_MICROPHONES][N_SAMPLES] frame (the reference's receiver,

@@ -436,6 +436,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the MISO / e2e extras")
     ap.add_argument("--exact-sum", type=int, default=1)
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: fused kernel + NVLink peer stores (p2p) or kernel then NCCL all-gather (nccl)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -508,8 +510,13 @@ def main():
     # ---- direction shard of this rank --------------------------------------------------------
     from lib.sharded import shard_bounds
     per, d_begin, d_count = shard_bounds(D, world, rank)
-    pipe = None
-    if world > 1:
+    pipe, peer = None, None
+    if world > 1 and args.gather == "p2p":
+        from lib.sharded import PeerGather
+        peer = PeerGather(D, F, rank, world, dist, depth=int(os.environ.get("BF_GATHER_DEPTH", "2")))   # kernel stores into every rank's buffer
+        d_maps = torch.zeros((F, D), device="cuda")
+        fs, ds = D, 1
+    elif world > 1:
         from lib.sharded import GatherPipeline
         pipe = GatherPipeline(D, F, rank, world, torch.device("cuda"), dist)   # direction-major, gather in place
         d_maps = pipe.bufs[0]
@@ -521,6 +528,9 @@ def main():
 
     def step(i):
         sig = d_pool[i % pool]
+        if peer:
+            peer.step(i, algo, sig, d_mics, n, stream)
+            return
         out = pipe.begin(i) if pipe else d_maps
         nat.check(L.bf_mimo_dev_ex(algo, sig.data_ptr(), out.data_ptr(), F, d_mics.data_ptr(), n,
                                    d_begin, d_count, fs, ds, 0, stream))
@@ -548,6 +558,8 @@ def main():
         ev[i][1].record()
     if pipe:
         pipe.finish()                 # the last gathers are part of the timed region
+    if peer:
+        peer.ready(args.warmup + args.steps - 1)      # every rank's last slice has arrived
     ev_end = torch.cuda.Event(enable_timing=True)
     ev_end.record()
     barrier()
@@ -565,6 +577,18 @@ def main():
 
     # ---- sharded result check: the gathered maps of the last step == all directions on one GPU
     gather_check = None
+    if peer:
+        peer.check()
+        last = args.warmup + args.steps - 1
+        full = torch.zeros((F, D), device="cuda")
+        nat.check(L.bf_mimo_dev_ex(algo, d_pool[last % pool].data_ptr(), full.data_ptr(), F, d_mics.data_ptr(), n,
+                                   0, D, D, 1, 0, stream))
+        torch.cuda.synchronize()
+        got = peer.maps(last)
+        ok = torch.tensor([1 if torch.equal(full, got) else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        gather_check = "bit-exact on every rank" if int(ok) else "MISMATCH"
+        d_maps = got.contiguous()
     if pipe and rank == 0:
         last = args.warmup + args.steps - 1
         full = torch.zeros((per * world, F), device="cuda")
@@ -658,7 +682,7 @@ def main():
                 replay = {"error": str(e)}
         if rank == 0 and args.workload == "c3":
             try:
-                hm = d_maps if world == 1 else d_maps[:D].t().contiguous()     # [F][D] power maps of the last step
+                hm = d_maps if (world == 1 or peer) else d_maps[:D].t().contiguous()   # [F][D] maps of the last step
                 heat = heatmap_c5(torch, hm, hbm_peak)
             except Exception as e:  # noqa: BLE001
                 heat = {"error": str(e)}
@@ -686,7 +710,8 @@ def main():
                        "mics": n, "samples": N, "l2": "inputs larger than L2 (pool of %d batches, %.0f MB)"
                        % (pool, pool * F * frame_bytes / 1e6),
                        "parallelism": "directions sharded over %d rank(s)%s" % (
-                           world, ", one in-place NCCL all-gather per step on a second stream, overlapping the next step's kernel" if world > 1 else ""),
+                           world, (", all-gather fused into the kernel: epilogue stores go to every rank's buffer over NVLink peer memory"
+                            if peer else ", one in-place NCCL all-gather per step on a second stream") if world > 1 else ""),
                        "exact_sum": args.exact_sum},
             "sum_step_ms": dev_ms, "wall_s": t_wall, "gather_check": gather_check, "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "miso": miso, "mvdr": mvdr, "replay": replay, "heatmap": heat, "fir": fir,

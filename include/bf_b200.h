@@ -246,6 +246,35 @@ int bf_ingest_dev(const int *d_stream, float *d_signals, int frames, int n_array
 int bf_window_dev(const float *d_recording, long samples, const long *d_starts, int frames,
                   float *d_frames, void *stream);
 
+/* ---- fused power maps + all-gather over NVLink peer memory -----------------------
+ * One process per GPU.  Every rank allocates a gather buffer float [world][frames][per_rank] and
+ * a flag array int64 [world] with bf_dev_alloc, exports both (bf_ipc_export), exchanges the
+ * 64-byte handles with its peers (any transport; lib/sharded.py uses torch.distributed) and opens
+ * theirs (bf_ipc_open).  bf_mimo_dev_gather then computes this rank's direction slice and stores
+ * every finished value into slice `rank` of ALL `world` buffers (its own and, through NVLink P2P
+ * stores issued by the kernel's epilogue, its peers') -- no collective call on the data path.
+ * bf_gather_signal publishes "step complete" into every rank's flag array after the kernel;
+ * bf_gather_wait blocks the stream until all ranks published `step` (sets *d_timed_out after ~20 s
+ * instead of hanging).  Only the tiled pad / lerp kernels (N_SAMPLES 64/128/256) store to peers. */
+int bf_dev_alloc(size_t bytes, void **d_ptr);            /* cudaMalloc + zero fill (exportable) */
+int bf_dev_free(void *d_ptr);
+int bf_ipc_export(void *d_ptr, unsigned char *handle64);
+int bf_ipc_open(const unsigned char *handle64, void **d_ptr);
+int bf_ipc_close(void *d_ptr);
+int bf_mimo_dev_gather(int algo, const float *d_signals, int frames, const int *d_mic_ids, int n,
+                       int d_begin, int d_count, int rank, int world, void *const *gather_bufs,
+                       long per_rank, void *stream);
+/* Same, with the step flags handled inside the kernel (no extra launches): before its first peer
+ * store a warp waits until every rank published wait_seq (0 = do not wait); the last CTA to finish
+ * publishes signal_seq into every rank's flag array (0 = do not signal). */
+int bf_mimo_dev_gather_sync(int algo, const float *d_signals, int frames, const int *d_mic_ids, int n,
+                            int d_begin, int d_count, int rank, int world, void *const *gather_bufs,
+                            long per_rank, void *const *flag_arrays, long long wait_seq, long long signal_seq,
+                            int *d_timed_out, void *stream);
+int bf_gather_signal(void *const *flag_arrays /* host array of `world` device pointers */, int world, int rank,
+                     long long step, void *stream);
+int bf_gather_wait(const void *d_my_flags, int world, long long step, int *d_timed_out, void *stream);
+
 /* ---- heat-map post-processing (SURVEY 8f "next" #2) -----------------------------------------
  * The step after the beamformer: PC/src/visual.py:130-171 calculate_heatmap (log scale),
  * 173-205 calculate_heatmap_fft (linear), 293-322 find_power_center, 227-291

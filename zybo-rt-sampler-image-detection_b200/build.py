@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libbf_b200.so")
 SOURCES = ["bf_api.cu", "bf_tables.cu", "das_mimo.cu", "das_simple.cu", "das_miso.cu", "das_fir.cu"]
-OPTIONAL = ["fd_path.cu", "fd_mvdr.cu", "fd_tc.cu", "ingest.cu", "heatmap.cu", "kf_host.cu"]
+OPTIONAL = ["fd_path.cu", "fd_mvdr.cu", "fd_tc.cu", "ingest.cu", "heatmap.cu", "kf_host.cu", "peer_gather.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

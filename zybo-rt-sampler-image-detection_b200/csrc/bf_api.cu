@@ -386,6 +386,75 @@ int bf_mimo_dev_ex(int algo, const float *d_signals, float *d_images, int frames
                          ImgLayout{frame_stride, dir_stride, d_origin}, (cudaStream_t)stream);
 }
 
+// Fused power maps + all-gather: this rank's direction slice, stored into the gather buffer of
+// every rank (layout per buffer: float [world][frames][per_rank]; slice r belongs to rank r).
+int bf_mimo_dev_gather(int algo, const float *d_signals, int frames, const int *d_mic_ids, int n,
+                       int d_begin, int d_count, int rank, int world, void *const *gather_bufs,
+                       long per_rank, void *stream)
+{
+    return bf_mimo_dev_gather_sync(algo, d_signals, frames, d_mic_ids, n, d_begin, d_count, rank, world, gather_bufs,
+                                   per_rank, nullptr, 0, 0, nullptr, stream);
+}
+
+int bf_mimo_dev_gather_sync(int algo, const float *d_signals, int frames, const int *d_mic_ids, int n,
+                            int d_begin, int d_count, int rank, int world, void *const *gather_bufs,
+                            long per_rank, void *const *flag_arrays, long long wait_seq, long long signal_seq,
+                            int *d_timed_out, void *stream)
+{
+    clear_error();
+    State &S = state();
+    int rc = ensure_device();
+    if (rc) return rc;
+    if ((rc = check_n(n, "bf_mimo_dev_gather"))) return rc;
+    const int D = S.cfg.max_res_x * S.cfg.max_res_y;
+    const int N = S.cfg.n_samples;
+    if (frames < 1 || d_begin < 0 || d_count < 0 || d_begin + d_count > D || !d_signals || !d_mic_ids ||
+        !gather_bufs || world < 1 || world > 8 || rank < 0 || rank >= world || per_rank < d_count) {
+        set_error(BF_ERR_ARG, "bf_mimo_dev_gather: frames %d slice [%d,+%d) of D=%d rank %d/%d per_rank %ld", frames,
+                  d_begin, d_count, D, rank, world, per_rank);
+        return BF_ERR_ARG;
+    }
+    if (!((algo == BF_ALGO_PAD || algo == BF_ALGO_LERP) && !S.simple_kernel && (N == 64 || N == 128 || N == 256))) {
+        set_error(BF_ERR_CONFIG, "bf_mimo_dev_gather: only the tiled pad / lerp kernels store to peers");
+        return BF_ERR_CONFIG;
+    }
+    if ((wait_seq > 0 || signal_seq > 0) && (!flag_arrays || !d_timed_out)) {
+        set_error(BF_ERR_ARG, "bf_mimo_dev_gather_sync: flags requested without flag arrays");
+        return BF_ERR_ARG;
+    }
+    if (d_count == 0) {
+        // nothing to compute on this rank, but its peers still wait for its flag
+        if (signal_seq > 0) return bf_gather_signal(flag_arrays, world, rank, signal_seq, stream);
+        return BF_OK;
+    }
+    ImgLayout lay{};
+    if (wait_seq > 0 || signal_seq > 0) {
+        if ((rc = S.d_done_counter.ensure(sizeof(unsigned int)))) return rc;
+        static bool zeroed = false;
+        if (!zeroed) { BF_CUDA(cudaMemset(S.d_done_counter.p, 0, sizeof(unsigned int))); zeroed = true; }
+        lay.flags_local = (long long *)flag_arrays[rank];
+        lay.wait_seq = wait_seq;
+        lay.signal_seq = signal_seq;
+        lay.world = world;
+        lay.flag_rank = rank;
+        lay.done_counter = S.d_done_counter.as<unsigned int>();
+        lay.timed_out = d_timed_out;
+        for (int r = 0; r < world; r++) lay.flags_all[r] = (long long *)flag_arrays[r];
+    }
+    lay.frame_stride = per_rank;
+    lay.dir_stride = 1;
+    lay.d_origin = d_begin;
+    const size_t slice = (size_t)rank * frames * per_rank;
+    float *own = nullptr;
+    for (int r = 0; r < world; r++) {
+        if (!gather_bufs[r]) { set_error(BF_ERR_ARG, "bf_mimo_dev_gather: null buffer for rank %d", r); return BF_ERR_ARG; }
+        float *dst = (float *)gather_bufs[r] + slice;
+        if (r == rank) own = dst;
+        else lay.peers[lay.n_peers++] = dst;
+    }
+    return mimo_tiled(algo, d_signals, own, frames, d_mic_ids, n, d_begin, d_count, lay, (cudaStream_t)stream);
+}
+
 int bf_miso_dev(int algo, const float *d_signals, float *d_out, int blocks, const int *d_mic_ids,
                 int n, int offset, int scale, void *stream)
 {

@@ -90,6 +90,7 @@ struct State {
     int exact_sum = 1;
     int sm_count = 0;
     int device = -1;
+    DevBuf d_done_counter;       // last-CTA ticket of the fused gather kernel
 };
 
 State &state();
@@ -100,7 +101,18 @@ int ensure_pinned(size_t bytes);
 int launch_max_abs_i32(const int *d, size_t count, int *h_max);   // bf_tables.cu
 
 // where the power of (frame f, direction d) goes: img[f*frame_stride + (d-d_origin)*dir_stride]
-struct ImgLayout { long frame_stride; long dir_stride; int d_origin; };
+struct ImgLayout {
+    long frame_stride; long dir_stride; int d_origin;
+    // fused all-gather: the same element is also stored into these buffers (other GPUs' memory
+    // mapped through CUDA IPC / NVLink peer access), same layout as the primary one
+    float *peers[7]; int n_peers;
+    // step flags of the fused gather (all optional): before its first peer store a warp waits until
+    // flags_local[r] >= wait_seq for every rank r; the last CTA to finish publishes signal_seq into
+    // flags_all[r][flag_rank] of every rank
+    long long *flags_local; long long wait_seq;
+    long long *flags_all[8]; int world, flag_rank; long long signal_seq;
+    unsigned int *done_counter; int *timed_out;
+};
 int mimo_tiled(int algo, const float *d_sig, float *d_img, int frames, const int *d_mics, int n,
                int d_begin, int d_count, ImgLayout lay, cudaStream_t st);   // das_mimo.cu
 bool fir_tiled_supported(int algo, int N, int T);                           // das_fir.cu

@@ -140,6 +140,11 @@ struct MimoParams {
     int n, n_mics_total, d_begin, d_count, frames;
     long img_fs, img_ds;     // output strides (frame, direction)
     int d_origin;
+    float *peers[7];         // fused all-gather targets (peer GPUs), same layout as img
+    int n_peers;
+    long long *flags_local; long long wait_seq;      // see ImgLayout
+    long long *flags_all[8]; int world, flag_rank; long long signal_seq;
+    unsigned int *done_counter; int *timed_out;
     int groups;              // groups per frame
     int tiles_per_frame, total_tiles;
     int W;                   // consumer warps
@@ -245,7 +250,7 @@ __device__ __forceinline__ void process_mic(float2 (&acc)[kR][J / 2], const uint
     }
 }
 
-template <int J, bool LERP, bool EXACT, bool PACK>
+template <int J, bool LERP, bool EXACT, bool PACK, bool GATHER>
 __global__ void __launch_bounds__((kMaxWarps + 1) * 32, 1) das_mimo_kernel(const MimoParams p)
 {
     constexpr int N = J * 32;
@@ -261,6 +266,7 @@ __global__ void __launch_bounds__((kMaxWarps + 1) * 32, 1) das_mimo_kernel(const
 
     uint64_t *full = (uint64_t *)smem;                   // [kStages]
     uint64_t *empty = full + kStages;                    // [kStages]
+    unsigned int *warps_done = (unsigned int *)(smem + 96);   // fused gather: consumer warps finished
     unsigned char *stages = smem + 128;
     float *scratch_all = (float *)(stages + kStages * stage_bytes);
 
@@ -277,6 +283,7 @@ __global__ void __launch_bounds__((kMaxWarps + 1) * 32, 1) das_mimo_kernel(const
                 bfptx::mbar_init(&empty[s], W);
             }
             bfptx::fence_mbar_init();
+            if (GATHER) *warps_done = 0u;
         }
     }
     __syncthreads();
@@ -343,6 +350,7 @@ __global__ void __launch_bounds__((kMaxWarps + 1) * 32, 1) das_mimo_kernel(const
 
     int s = 0;
     uint32_t ph = 0;
+    bool peers_ready = false;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int frame = tile / p.tiles_per_frame;
         const int g = group_of(tile);
@@ -399,6 +407,21 @@ __global__ void __launch_bounds__((kMaxWarps + 1) * 32, 1) das_mimo_kernel(const
 
         if (!active) continue;
 
+        // fused gather: the peers' buffers may be overwritten only after every rank published wait_seq
+        if (GATHER && p.wait_seq > 0 && !peers_ready) {
+            if (lane < p.world) {
+                const volatile long long *f = p.flags_local + lane;
+                long long spins = 0;
+                while (*f < p.wait_seq) {
+                    __nanosleep(100);
+                    if (++spins > 100000000LL) { *p.timed_out = 1; break; }
+                }
+            }
+            __threadfence_system();
+            __syncwarp();
+            peers_ready = true;
+        }
+
         // ---- epilogue: out/n, square, sum over t, /N (pad_and_sum.c:122-131) ----
         float *img = p.img + (long)frame * p.img_fs + (long)(p.d_begin + g * kR - p.d_origin) * p.img_ds;
         const int valid = min(kR, p.d_count - g * kR);
@@ -429,7 +452,12 @@ __global__ void __launch_bounds__((kMaxWarps + 1) * 32, 1) das_mimo_kernel(const
                 }
                 __syncwarp();
             }
-            if (lane < valid) img[lane * ds] = __fmul_rn(run, 1.0f / (float)N);
+            if (lane < valid) {
+                const float v = __fmul_rn(run, 1.0f / (float)N);
+                img[lane * ds] = v;
+                if (GATHER)
+                    for (int q = 0; q < p.n_peers; q++) (p.peers[q] + (img - p.img))[lane * ds] = v;   // NVLink P2P store
+            }
         } else {
             float tot[kR];
 #pragma unroll
@@ -451,8 +479,30 @@ __global__ void __launch_bounds__((kMaxWarps + 1) * 32, 1) das_mimo_kernel(const
 #pragma unroll
             for (int r = 0; r < kR; r++)
                 if (lane == r) mine = tot[r];
-            if (lane < valid) img[lane * ds] = __fmul_rn(mine, 1.0f / (float)N);
+            if (lane < valid) {
+                const float v = __fmul_rn(mine, 1.0f / (float)N);
+                img[lane * ds] = v;
+                if (GATHER)
+                    for (int q = 0; q < p.n_peers; q++) (p.peers[q] + (img - p.img))[lane * ds] = v;
+            }
             __syncwarp();
+        }
+    }
+
+    // fused gather: publish "step complete" once every warp of every CTA has finished its stores
+    if (GATHER && p.signal_seq > 0) {
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0 && atomicAdd(warps_done, 1u) == (unsigned)W - 1u) {
+            if (atomicAdd(p.done_counter, 1u) == gridDim.x - 1u) {
+                *p.done_counter = 0u;
+                __threadfence_system();
+                for (int r = 0; r < p.world; r++) {
+                    volatile long long *f = p.flags_all[r] + p.flag_rank;
+                    *f = p.signal_seq;
+                }
+                __threadfence_system();
+            }
         }
     }
 }
@@ -474,12 +524,16 @@ static int launch_J(bool lerp, bool exact, const MimoParams &mp, int grid, size_
         return BF_OK;
     };
     static const bool pack = getenv("BF_MIMO_PACKED") ? atoi(getenv("BF_MIMO_PACKED")) != 0 : true;
-    if (pack) {
-        if (lerp) return exact ? go(das_mimo_kernel<J, true, true, true>) : go(das_mimo_kernel<J, true, false, true>);
-        return exact ? go(das_mimo_kernel<J, false, true, true>) : go(das_mimo_kernel<J, false, false, true>);
+    if (mp.n_peers > 0 || mp.wait_seq > 0 || mp.signal_seq > 0) {      // fused all-gather variant
+        if (lerp) return exact ? go(das_mimo_kernel<J, true, true, true, true>) : go(das_mimo_kernel<J, true, false, true, true>);
+        return exact ? go(das_mimo_kernel<J, false, true, true, true>) : go(das_mimo_kernel<J, false, false, true, true>);
     }
-    if (lerp) return exact ? go(das_mimo_kernel<J, true, true, false>) : go(das_mimo_kernel<J, true, false, false>);
-    return exact ? go(das_mimo_kernel<J, false, true, false>) : go(das_mimo_kernel<J, false, false, false>);
+    if (pack) {
+        if (lerp) return exact ? go(das_mimo_kernel<J, true, true, true, false>) : go(das_mimo_kernel<J, true, false, true, false>);
+        return exact ? go(das_mimo_kernel<J, false, true, true, false>) : go(das_mimo_kernel<J, false, false, true, false>);
+    }
+    if (lerp) return exact ? go(das_mimo_kernel<J, true, true, false, false>) : go(das_mimo_kernel<J, true, false, false, false>);
+    return exact ? go(das_mimo_kernel<J, false, true, false, false>) : go(das_mimo_kernel<J, false, false, false, false>);
 }
 
 int mimo_tiled(int algo, const float *d_sig, float *d_img, int frames, const int *d_mics, int n,
@@ -528,6 +582,11 @@ int mimo_tiled(int algo, const float *d_sig, float *d_img, int frames, const int
     mp.offs = gt->offs.as<uint4>(); mp.wts = gt->wts.as<float>();
     mp.n = n; mp.n_mics_total = S.cfg.n_microphones;
     mp.img_fs = lay.frame_stride; mp.img_ds = lay.dir_stride; mp.d_origin = lay.d_origin;
+    mp.n_peers = lay.n_peers;
+    mp.flags_local = lay.flags_local; mp.wait_seq = lay.wait_seq; mp.world = lay.world; mp.flag_rank = lay.flag_rank;
+    mp.signal_seq = lay.signal_seq; mp.done_counter = lay.done_counter; mp.timed_out = lay.timed_out;
+    for (int r = 0; r < lay.world && r < 8; r++) mp.flags_all[r] = lay.flags_all[r];
+    for (int q = 0; q < lay.n_peers && q < 7; q++) mp.peers[q] = lay.peers[q];
     mp.d_begin = d_begin; mp.d_count = d_count; mp.frames = frames;
     mp.groups = gt->groups;
     mp.P = P;

@@ -80,6 +80,16 @@ def lib():
     L.bf_ingest_dev.argtypes = [vp, vp, ci, ci, ci, ci, cd, ci, vp, vp]
     L.bf_window_dev.argtypes = [vp, ctypes.c_long, vp, ci, vp, vp]
     cf, cl = ctypes.c_float, ctypes.c_long
+    cll = ctypes.c_longlong
+    L.bf_dev_alloc.argtypes = [cs, ctypes.POINTER(vp)]
+    L.bf_dev_free.argtypes = [vp]
+    L.bf_ipc_export.argtypes = [vp, vp]
+    L.bf_ipc_open.argtypes = [vp, ctypes.POINTER(vp)]
+    L.bf_ipc_close.argtypes = [vp]
+    L.bf_mimo_dev_gather.argtypes = [ci, vp, ci, vp, ci, ci, ci, ci, ci, vp, ctypes.c_long, vp]
+    L.bf_mimo_dev_gather_sync.argtypes = [ci, vp, ci, vp, ci, ci, ci, ci, ci, vp, ctypes.c_long, vp, cll, cll, vp, vp]
+    L.bf_gather_signal.argtypes = [vp, ci, ci, cll, vp]
+    L.bf_gather_wait.argtypes = [vp, ci, cll, vp, vp]
     L.bf_kf_create.restype = vp
     L.bf_kf_destroy.argtypes = [vp]
     L.bf_kf_destroy.restype = None

@@ -100,6 +100,122 @@ class GatherPipeline:
         self.torch.cuda.current_stream().wait_stream(self.comm)
 
 
+class _DevArray:
+    """Device allocation owned by the library, visible to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.ptr = ptr
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+class PeerGather:
+    """Fused power maps + all-gather over NVLink peer memory (no collective on the data path).
+
+    Every rank owns `depth` gather buffers float [world][F][per] and one flag array; the buffers of
+    all ranks are mapped into every process through CUDA IPC (handles exchanged once with
+    torch.distributed -- plumbing only).  step(i, ...) launches the tiled kernel, whose epilogue
+    stores each finished value into slice `rank` of all `world` buffers, then publishes step i to
+    every rank's flags.  Buffer i % depth is overwritten by step i + depth: the writers first wait
+    (inside the kernel) until every rank has published step i + 1 + consume_lag, so whatever reads the
+    maps of step i must be enqueued on the compute stream before step i + 1 + consume_lag is launched
+    (consume_lag = 0: consume right after the step; 1: consume while the next step runs; needs
+    depth >= consume_lag + 2).  maps(i) is the assembled [F][D] tensor of step i.
+    """
+
+    def __init__(self, n_directions, frames, rank, world, dist, depth=2, consume_lag=0):
+        import ctypes
+        if depth < consume_lag + 2:
+            raise ValueError("PeerGather: depth must be at least consume_lag + 2")
+        self.consume_lag = consume_lag
+        import torch
+        from . import _native
+        self.torch, self.nat, self.L = torch, _native, _native.lib()
+        self.D, self.F, self.rank, self.world, self.depth = n_directions, frames, rank, world, depth
+        self.per, self.d_begin, self.d_count = shard_bounds(n_directions, world, rank)
+        L = self.L
+        vp = ctypes.c_void_p
+        n_buf = world * frames * self.per
+
+        def alloc(nbytes):
+            out = vp()
+            _native.check(L.bf_dev_alloc(ctypes.c_size_t(nbytes), ctypes.byref(out)))
+            return out.value
+        self.own = [alloc(n_buf * 4) for _ in range(depth)]
+        self.own_flags = alloc(8 * 8)
+        handles = []
+        for ptr in self.own + [self.own_flags]:
+            h = (ctypes.c_ubyte * 64)()
+            _native.check(L.bf_ipc_export(vp(ptr), h))
+            handles.append(bytes(h))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, handles)
+        self.bufs = [[None] * world for _ in range(depth)]      # [depth][rank] device pointers
+        self.flags = [None] * world
+        self._opened = []
+        for r in range(world):
+            for k in range(depth + 1):
+                if r == rank:
+                    ptr = (self.own + [self.own_flags])[k]
+                else:
+                    out = vp()
+                    hb = (ctypes.c_ubyte * 64).from_buffer_copy(everyone[r][k])
+                    _native.check(L.bf_ipc_open(hb, ctypes.byref(out)))
+                    ptr = out.value
+                    self._opened.append(ptr)
+                if k < depth:
+                    self.bufs[k][r] = ptr
+                else:
+                    self.flags[r] = ptr
+        self._buf_arrays = [(vp * world)(*[vp(x) for x in self.bufs[k]]) for k in range(depth)]
+        self._flag_array = (vp * world)(*[vp(x) for x in self.flags])
+        self.views = [torch.as_tensor(_DevArray(self.own[k], (world, frames, self.per), "<f4"), device="cuda")
+                      for k in range(depth)]
+        self.timed_out = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self._seq = 0
+        self._seq_of = {}
+        dist.barrier()
+
+    def step(self, i, algo, d_signals, d_mic_ids, n, stream=None):
+        """Launch step i (i must increase by one per call): ONE kernel that computes the slice, stores it
+        into every rank's buffer and publishes the step.  Before its first store into buffer i % depth it
+        waits (inside the kernel) until every rank has published step i - depth + 1, i.e. has enqueued
+        everything that reads that buffer's previous contents."""
+        nat, L = self.nat, self.L
+        st = stream if stream is not None else self.torch.cuda.current_stream().cuda_stream
+        self._seq += 1
+        seq = self._seq
+        self._seq_of[i] = seq
+        k = i % self.depth
+        wait_seq = max(0, seq - self.depth + 1 + self.consume_lag)
+        nat.check(L.bf_mimo_dev_gather_sync(algo, d_signals.data_ptr(), self.F, d_mic_ids.data_ptr(), n,
+                                            self.d_begin, self.d_count, self.rank, self.world, self._buf_arrays[k],
+                                            self.per, self._flag_array, wait_seq, seq, self.timed_out.data_ptr(), st))
+
+    def ready(self, i, stream=None):
+        """Make the stream wait until every rank's slice of step i has arrived; returns the
+        [world][F][per] view of that step."""
+        st = stream if stream is not None else self.torch.cuda.current_stream().cuda_stream
+        self.nat.check(self.L.bf_gather_wait(self.flags[self.rank], self.world, self._seq_of[i],
+                                             self.timed_out.data_ptr(), st))
+        return self.views[i % self.depth]
+
+    def maps(self, i):
+        """[F][D] tensor of step i (a copy: the gather layout is [rank][F][per]); waits for the step."""
+        v = self.ready(i)
+        return v.permute(1, 0, 2).reshape(self.F, self.world * self.per)[:, :self.D]
+
+    def check(self):
+        if int(self.timed_out.item()):
+            raise RuntimeError("PeerGather: a peer did not publish its step within the spin limit")
+
+    def close(self):
+        import ctypes
+        self.torch.cuda.synchronize()
+        for ptr in self._opened:
+            self.L.bf_ipc_close(ctypes.c_void_p(ptr))
+        self._opened = []
+
+
 def assemble_reference(slices, n_directions):
     """NumPy model of the gather: list of per-rank [per][F] arrays -> [D][F]."""
     return np.concatenate(slices, axis=0)[:n_directions]

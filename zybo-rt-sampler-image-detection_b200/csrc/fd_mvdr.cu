@@ -194,6 +194,164 @@ __global__ void mvdr_trinv_kernel(const double2 *__restrict__ chol, int M, float
     }
 }
 
+// ---- blocked versions (M <= 256, one thread per row / column) ---------------------------------
+// The column-by-column kernels above re-read the whole factor for every column (M^3/3 x 16 B per
+// bin from L2: 45 GB per C4 map, L2-bandwidth bound).  Here a thread streams its row of L (its
+// column of Z) once per PANEL of NB columns (rows) and keeps NB complex accumulators in registers;
+// the NB pivot rows are broadcast from shared memory.  Same arithmetic, different summation order.
+static constexpr int kNB = 8;       // panel width
+static constexpr int kKC = 64;      // k-chunk staged in shared memory
+
+__global__ void __launch_bounds__(256) mvdr_chol_blocked_kernel(double2 *__restrict__ cov, int M, int *__restrict__ fail)
+{
+    double2 *R = cov + (size_t)blockIdx.x * M * M;
+    __shared__ double2 pan[kNB][kKC];          // L[j0+c][k0 .. k0+KC)
+    __shared__ double2 lrow[kNB];              // L[j0+c'][j] of the column being finished
+    __shared__ double pivot;
+    const int i = threadIdx.x;
+    for (int j0 = 0; j0 < M; j0 += kNB) {
+        const int nb = min(kNB, M - j0);
+        const bool live = i >= j0 && i < M;
+        double sx[kNB], sy[kNB];
+#pragma unroll
+        for (int c = 0; c < kNB; c++) {
+            sx[c] = 0.0; sy[c] = 0.0;
+            if (live && c < nb) {
+                const double2 a = R[(size_t)(j0 + c) * M + i];       // A[i][j0+c] = conj(A[j0+c][i])
+                sx[c] = a.x; sy[c] = -a.y;
+            }
+        }
+        // s[c] -= sum_{k < j0} L[i][k] * conj(L[j0+c][k])
+        for (int k0 = 0; k0 < j0; k0 += kKC) {
+            const int kc = min(kKC, j0 - k0);
+            __syncthreads();
+            for (int t = threadIdx.x; t < kNB * kKC; t += blockDim.x) {
+                const int c = t / kKC, kk = t - c * kKC;
+                pan[c][kk] = (c < nb && kk < kc) ? R[(size_t)(k0 + kk) * M + (j0 + c)] : make_double2(0.0, 0.0);
+            }
+            __syncthreads();
+            if (live) {
+#pragma unroll 4
+                for (int kk = 0; kk < kc; kk++) {
+                    const double2 a = R[(size_t)(k0 + kk) * M + i];
+#pragma unroll
+                    for (int c = 0; c < kNB; c++) {
+                        const double2 b = pan[c][kk];
+                        sx[c] -= a.x * b.x + a.y * b.y;
+                        sy[c] -= a.y * b.x - a.x * b.y;
+                    }
+                }
+            }
+        }
+        // factor the panel: column j = j0 + c
+#pragma unroll
+        for (int c = 0; c < kNB; c++) {
+            if (c < nb) {
+                const int j = j0 + c;
+                __syncthreads();
+                if (i == j) {
+                    double d2 = sx[c];
+                    if (!(d2 > 0.0)) { atomicExch(fail, 1); d2 = 1.0; }
+                    pivot = sqrt(d2);
+                }
+                __syncthreads();
+                const double d = pivot;
+                double lx = 0.0, ly = 0.0;
+                if (live && i >= j) {
+                    lx = (i == j) ? d : sx[c] / d;
+                    ly = (i == j) ? 0.0 : sy[c] / d;
+                    R[(size_t)j * M + i] = make_double2(lx, ly);     // L[i][j] at [j][i]
+                    if (i < j0 + nb) lrow[i - j0] = make_double2(lx, ly);
+                }
+                __syncthreads();
+                if (live && i > j) {
+#pragma unroll
+                    for (int c2 = 0; c2 < kNB; c2++) {
+                        if (c2 > c && c2 < nb) {
+                            const double2 b = lrow[c2];              // L[j0+c2][j]
+                            sx[c2] -= lx * b.x + ly * b.y;
+                            sy[c2] -= ly * b.x - lx * b.y;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Z = L^-1, row panels of NB: thread c owns column c, acc[r] = sum_{k < i0} L[i0+r][k] Z[k][c]
+__global__ void __launch_bounds__(256) mvdr_trinv_blocked_kernel(const double2 *__restrict__ chol, int M,
+                                                                  float2 *__restrict__ linv, double2 *__restrict__ work)
+{
+    const double2 *Lt = chol + (size_t)blockIdx.x * M * M;
+    double2 *Z = work + (size_t)blockIdx.x * M * M;
+    float2 *Zf = linv + (size_t)blockIdx.x * M * M;
+    __shared__ double2 pan[kNB][kKC];          // L[i0+r][k0 .. k0+KC)
+    __shared__ double2 tri[kNB][kNB];          // L[i0+r][i0+r']
+    const int c = threadIdx.x;
+    const int cw = c & ~31;                    // first column of this warp: Z[k][c] = 0 for k < c
+    for (int i0 = 0; i0 < M; i0 += kNB) {
+        const int nb = min(kNB, M - i0);
+        double ax[kNB], ay[kNB];
+#pragma unroll
+        for (int r = 0; r < kNB; r++) { ax[r] = 0.0; ay[r] = 0.0; }
+        for (int k0 = 0; k0 < i0; k0 += kKC) {
+            const int kc = min(kKC, i0 - k0);
+            __syncthreads();
+            for (int t = threadIdx.x; t < kNB * kKC; t += blockDim.x) {
+                const int r = t / kKC, kk = t - r * kKC;
+                pan[r][kk] = (r < nb && kk < kc) ? Lt[(size_t)(k0 + kk) * M + (i0 + r)] : make_double2(0.0, 0.0);
+            }
+            __syncthreads();
+            if (c < M && cw < k0 + kc) {
+                const int kb = max(0, cw - k0);
+#pragma unroll 4
+                for (int kk = kb; kk < kc; kk++) {
+                    const double2 z = Z[(size_t)(k0 + kk) * M + c];
+#pragma unroll
+                    for (int r = 0; r < kNB; r++) {
+                        const double2 a = pan[r][kk];
+                        ax[r] += a.x * z.x - a.y * z.y;
+                        ay[r] += a.x * z.y + a.y * z.x;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < kNB * kNB; t += blockDim.x) {
+            const int r = t / kNB, r2 = t - r * kNB;
+            tri[r][r2] = (r < nb && r2 <= r) ? Lt[(size_t)(i0 + r2) * M + (i0 + r)] : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        if (c < M) {
+            double zx[kNB], zy[kNB];
+#pragma unroll
+            for (int r = 0; r < kNB; r++) {
+                zx[r] = 0.0; zy[r] = 0.0;
+                if (r < nb) {
+                    const int i = i0 + r;
+                    if (c <= i) {
+                        double px = (c == i ? 1.0 : 0.0) - ax[r], py = -ay[r];
+#pragma unroll
+                        for (int r2 = 0; r2 < kNB; r2++) {
+                            if (r2 < r) {
+                                const double2 a = tri[r][r2];
+                                px -= a.x * zx[r2] - a.y * zy[r2];
+                                py -= a.x * zy[r2] + a.y * zx[r2];
+                            }
+                        }
+                        const double dii = tri[r][r].x;
+                        zx[r] = px / dii;
+                        zy[r] = py / dii;
+                    }
+                    Z[(size_t)i * M + c] = make_double2(zx[r], zy[r]);
+                    Zf[(size_t)i * M + c] = make_float2((float)zx[r], (float)zy[r]);
+                }
+            }
+        }
+    }
+}
+
 // ---- steering: P[d] = sum_f 1 / || L_f^-1 a_f(d) ||^2, CUDA-core fp32 --------------------------
 // CTA = TD directions; per bin the TD x M phasors are generated once into shared memory
 // ([m][d], float2), then rows of L^-1 stream through shared memory in chunks of RC rows.
@@ -279,9 +437,15 @@ int mvdr_dev(const float *d_snap, float *d_power, int K, double delta, cudaStrea
     static DevBuf cov_copy;
     if ((rc = cov_copy.ensure((size_t)F * M * M * sizeof(double2)))) { return rc; }
     cudaMemcpyAsync(cov_copy.p, S.cov.p, (size_t)F * M * M * sizeof(double2), cudaMemcpyDeviceToDevice, st);
-    mvdr_chol_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, fail.as<int>());
+    // blocked float64 factorisation / inverse (one thread per row); BF_MVDR_BLOCKED=0 selects the
+    // column-by-column kernels
+    const bool blocked = M <= 256 && !(getenv("BF_MVDR_BLOCKED") && atoi(getenv("BF_MVDR_BLOCKED")) == 0);
+    const int mt = (M + 31) / 32 * 32;
+    if (blocked) mvdr_chol_blocked_kernel<<<F, mt, 0, st>>>(S.cov.as<double2>(), M, fail.as<int>());
+    else mvdr_chol_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, fail.as<int>());
     cudaEventRecord(ev[3], st);
-    mvdr_trinv_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, S.linv.as<float2>(), work.as<double2>());
+    if (blocked) mvdr_trinv_blocked_kernel<<<F, mt, 0, st>>>(S.cov.as<double2>(), M, S.linv.as<float2>(), work.as<double2>());
+    else mvdr_trinv_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, S.linv.as<float2>(), work.as<double2>());
     cudaEventRecord(ev[4], st);
     const double bin_hz = (double)(int)((int)G.fs / 2) / (double)(G.N / 2);
     // steering contraction: tcgen05 tensor-core kernel (fd_tc.cu) for 256 microphones, CUDA-core

@@ -72,19 +72,53 @@ __global__ void mvdr_rfft64_kernel(const float *__restrict__ sig, const int *__r
 }
 
 // ---- covariance R_f[i][j] = 1/K sum_k X_k[f,i] conj(X_k[f,j]) -------------------------------
-__global__ void mvdr_cov_kernel(const double2 *__restrict__ spec, int K, int F, int M,
-                                double2 *__restrict__ cov)
+// A 16x16-thread CTA computes a 64x64 tile of R_f, every thread a 4x4 block; the
+// snapshots of the tile's rows and columns go through shared memory 16 at a time.  Same
+// ascending-k order per element; explicit fma (the library is built with --fmad=false).
+__global__ void __launch_bounds__(256) mvdr_cov_tiled_kernel(const double2 *__restrict__ spec, int K, int F, int M,
+                                                             double2 *__restrict__ cov)
 {
+    constexpr int TB = 64, KC = 16;
+    __shared__ double2 xi[KC][TB], xj[KC][TB];
     const int f = blockIdx.z;
-    const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
-    if (i >= M || j >= M) return;
-    double re = 0.0, im = 0.0;
-    for (int k = 0; k < K; k++) {
-        const double2 a = spec[((size_t)k * F + f) * M + i], b = spec[((size_t)k * F + f) * M + j];
-        re += a.x * b.x + a.y * b.y;          // a * conj(b)
-        im += a.y * b.x - a.x * b.y;
+    const int i0 = blockIdx.y * TB, j0 = blockIdx.x * TB;
+    const int ty = threadIdx.y, tx = threadIdx.x, tid = ty * 16 + tx;
+    double re[4][4], im[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) { re[a][b] = 0.0; im[a][b] = 0.0; }
+    for (int k0 = 0; k0 < K; k0 += KC) {
+        __syncthreads();
+        for (int t = tid; t < KC * TB; t += 256) {
+            const int kk = t / TB, c = t - kk * TB;
+            const bool kv = k0 + kk < K;
+            const size_t base = ((size_t)(k0 + kk) * F + f) * M;
+            xi[kk][c] = (kv && i0 + c < M) ? spec[base + i0 + c] : make_double2(0.0, 0.0);
+            xj[kk][c] = (kv && j0 + c < M) ? spec[base + j0 + c] : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < KC; kk++) {
+            double2 a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { a[q] = xi[kk][ty + 16 * q]; b[q] = xj[kk][tx + 16 * q]; }
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    re[p][q] = fma(a[p].x, b[q].x, fma(a[p].y, b[q].y, re[p][q]));      // a * conj(b)
+                    im[p][q] = fma(a[p].y, b[q].x, fma(-a[p].x, b[q].y, im[p][q]));
+                }
+        }
     }
-    cov[((size_t)f * M + i) * M + j] = make_double2(re / K, im / K);
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = i0 + ty + 16 * p, j = j0 + tx + 16 * q;
+            if (i < M && j < M) cov[((size_t)f * M + i) * M + j] = make_double2(re[p][q] / K, im[p][q] / K);
+        }
 }
 
 // diagonal loading: R_ii += delta * tr(R)/M
@@ -237,8 +271,8 @@ __global__ void __launch_bounds__(256) mvdr_chol_blocked_kernel(double2 *__restr
 #pragma unroll
                     for (int c = 0; c < kNB; c++) {
                         const double2 b = pan[c][kk];
-                        sx[c] -= a.x * b.x + a.y * b.y;
-                        sy[c] -= a.y * b.x - a.x * b.y;
+                        sx[c] = fma(-a.x, b.x, fma(-a.y, b.y, sx[c]));
+                        sy[c] = fma(-a.y, b.x, fma(a.x, b.y, sy[c]));
                     }
                 }
             }
@@ -269,8 +303,8 @@ __global__ void __launch_bounds__(256) mvdr_chol_blocked_kernel(double2 *__restr
                     for (int c2 = 0; c2 < kNB; c2++) {
                         if (c2 > c && c2 < nb) {
                             const double2 b = lrow[c2];              // L[j0+c2][j]
-                            sx[c2] -= lx * b.x + ly * b.y;
-                            sy[c2] -= ly * b.x - lx * b.y;
+                            sx[c2] = fma(-lx, b.x, fma(-ly, b.y, sx[c2]));
+                            sy[c2] = fma(-ly, b.x, fma(lx, b.y, sy[c2]));
                         }
                     }
                 }
@@ -311,8 +345,8 @@ __global__ void __launch_bounds__(256) mvdr_trinv_blocked_kernel(const double2 *
 #pragma unroll
                     for (int r = 0; r < kNB; r++) {
                         const double2 a = pan[r][kk];
-                        ax[r] += a.x * z.x - a.y * z.y;
-                        ay[r] += a.x * z.y + a.y * z.x;
+                        ax[r] = fma(a.x, z.x, fma(-a.y, z.y, ax[r]));
+                        ay[r] = fma(a.x, z.y, fma(a.y, z.x, ay[r]));
                     }
                 }
             }
@@ -426,7 +460,7 @@ int mvdr_dev(const float *d_snap, float *d_power, int K, double delta, cudaStrea
     mvdr_rfft64_kernel<<<dim3(M, K), threads, 2 * G.N * sizeof(double2), st>>>(
         d_snap, G.active, M, G.n_mics, G.N, ilog2e(G.N), G.lo, G.hi, S.spec.as<double2>());
     cudaEventRecord(ev[1], st);
-    mvdr_cov_kernel<<<dim3((M + 15) / 16, (M + 15) / 16, F), dim3(16, 16), 0, st>>>(
+    mvdr_cov_tiled_kernel<<<dim3((M + 63) / 64, (M + 63) / 64, F), dim3(16, 16), 0, st>>>(
         S.spec.as<double2>(), K, F, M, S.cov.as<double2>());
     mvdr_load_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, delta);
     cudaEventRecord(ev[2], st);

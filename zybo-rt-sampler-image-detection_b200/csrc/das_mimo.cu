@@ -196,7 +196,7 @@ __device__ __forceinline__ void two_run(float2 (&acc)[kR][J / 2], const float2 (
 // One microphone into the 8 accumulators of the group.  `a` holds the row at the
 // entry's first offset when PRE (prefetched by the caller), else it is loaded here.
 template <int J, bool LERP, bool PACK, bool PRE>
-__device__ __forceinline__ void process_mic(float2 (&acc)[kR][J / 2], const uint4 e,
+__device__ __forceinline__ void process_mic(float2 (&acc)[kR][J / 2], const uint2 e, const uint4 *efull,
                                             const char *rowp, const size_t row_bytes,
                                             float2 (&a)[J / 2], const float *wrow)
 {
@@ -233,7 +233,8 @@ __device__ __forceinline__ void process_mic(float2 (&acc)[kR][J / 2], const uint
         }
     } else {
         // general: reload only when the delay changes from one direction to the next
-        const uint32_t ow[4] = {e.x, e.y, e.z, e.w};
+        const uint4 ef = *efull;
+        const uint32_t ow[4] = {ef.x, ef.y, ef.z, ef.w};
         uint32_t prev = oa;
 #pragma unroll
         for (int r = 0; r < kR; r++) {
@@ -377,27 +378,33 @@ __global__ void __launch_bounds__((kMaxWarps + 1) * 32, 1) das_mimo_kernel(const
             bfptx::mbar_wait(&full[s], ph);
             if (active) {
                 const char *rowp = (const char *)(stages + (size_t)s * stage_bytes) + lane * 4;
+                const uint2 *e2p = (const uint2 *)ebuf;          // first two words of entry i at e2p[2 * i]
                 if (PIPE) {
+                    // rows are loaded one microphone ahead, entries two ahead (an entry is needed for the
+                    // next row's address long before its own adds start)
                     float2 A[J / 2], B[J / 2];
-                    uint4 e0 = ebuf[0];
+                    uint2 e0 = e2p[0], e1 = e2p[2];
                     load_row<J>(rowp + (e0.x & 0xfffcu), A);
                     int mm = 0;
                     for (; mm + 1 < cnt; mm += 2) {
-                        const uint4 e1 = ebuf[mm + 1];
                         load_row<J>(rowp + mic_bytes + (e1.x & 0xfffcu), B);
-                        process_mic<J, LERP, PACK, true>(acc, e0, rowp, row_bytes, A, nullptr);
-                        if (mm + 2 < cnt) {
-                            e0 = ebuf[mm + 2];
-                            load_row<J>(rowp + 2 * mic_bytes + (e0.x & 0xfffcu), A);
-                        }
-                        process_mic<J, LERP, PACK, true>(acc, e1, rowp + mic_bytes, row_bytes, B, nullptr);
+                        const uint2 ea = e2p[2 * (mm + 2)];       // may run one or two entries past cnt: unused then
+                        process_mic<J, LERP, PACK, true>(acc, e0, ebuf + mm, rowp, row_bytes, A, nullptr);
+                        if (mm + 2 < cnt) load_row<J>(rowp + 2 * mic_bytes + (ea.x & 0xfffcu), A);
+                        const uint2 eb = e2p[2 * (mm + 3)];
+                        process_mic<J, LERP, PACK, true>(acc, e1, ebuf + mm + 1, rowp + mic_bytes, row_bytes, B, nullptr);
+                        e0 = ea; e1 = eb;
                         rowp += 2 * mic_bytes;
                     }
-                    if (mm < cnt) process_mic<J, LERP, PACK, true>(acc, e0, rowp, row_bytes, A, nullptr);
+                    if (mm < cnt) process_mic<J, LERP, PACK, true>(acc, e0, ebuf + mm, rowp, row_bytes, A, nullptr);
                 } else {
                     float2 A[J / 2];
-                    for (int mm = 0; mm < cnt; mm++, rowp += mic_bytes)
-                        process_mic<J, LERP, PACK, false>(acc, ebuf[mm], rowp, row_bytes, A, wbuf + mm * 8);
+                    uint2 en = e2p[0];
+                    for (int mm = 0; mm < cnt; mm++, rowp += mic_bytes) {
+                        const uint2 e = en;
+                        en = e2p[2 * (mm + 1)];                   // next entry in flight during this microphone
+                        process_mic<J, LERP, PACK, false>(acc, e, ebuf + mm, rowp, row_bytes, A, wbuf + mm * 8);
+                    }
                 }
             }
             __syncwarp();

@@ -267,8 +267,8 @@ __global__ void __launch_bounds__((kMaxWarps + 1) * 32, 1) das_mimo_kernel(const
 
     uint64_t *full = (uint64_t *)smem;                   // [kStages]
     uint64_t *empty = full + kStages;                    // [kStages]
-    unsigned int *warps_done = (unsigned int *)(smem + 96);   // fused gather: consumer warps finished
-    unsigned char *stages = smem + 128;
+    unsigned int *warps_done = (unsigned int *)(smem + 224);   // fused gather: consumer warps finished
+    unsigned char *stages = smem + 256;
     float *scratch_all = (float *)(stages + kStages * stage_bytes);
 
     // ---- prologue: zero the pad columns once, init barriers ----------------
@@ -611,7 +611,7 @@ int mimo_tiled(int algo, const float *d_sig, float *d_img, int frames, const int
     // stage geometry: as many mic rows per stage as fit in the smem budget (<= 32: one entry per lane)
     const size_t row_bytes = (size_t)(P + N) * 4 * (lerp ? 2 : 1);
     const size_t scratch_bytes = (size_t)W * kR * kScratchStride * 4;
-    const size_t budget = 227 * 1024 - 128 - scratch_bytes - 1024;
+    const size_t budget = 227 * 1024 - 256 - scratch_bytes - 1024;
     int Mt = 32;
     while (Mt > 1 && (size_t)Mt * row_bytes * kStages > budget) Mt >>= 1;
     if ((size_t)Mt * row_bytes * kStages > budget) {
@@ -620,7 +620,7 @@ int mimo_tiled(int algo, const float *d_sig, float *d_img, int frames, const int
     }
     if (Mt > n) Mt = n;
     mp.Mt = Mt;
-    const size_t smem = 128 + (size_t)kStages * Mt * row_bytes + scratch_bytes;
+    const size_t smem = 256 + (size_t)kStages * Mt * row_bytes + scratch_bytes;
 
     if (((uintptr_t)d_sig & 15) != 0) {
         set_error(BF_ERR_ARG, "signal buffer must be 16-byte aligned for bulk copies");

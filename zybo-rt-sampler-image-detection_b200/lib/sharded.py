@@ -173,6 +173,7 @@ class PeerGather:
         self.timed_out = torch.zeros(1, dtype=torch.int32, device="cuda")
         self._seq = 0
         self._seq_of = {}
+        self.dist_barrier = dist.barrier
         dist.barrier()
 
     def step(self, i, algo, d_signals, d_mic_ids, n, stream=None):
@@ -214,6 +215,11 @@ class PeerGather:
         for ptr in self._opened:
             self.L.bf_ipc_close(ctypes.c_void_p(ptr))
         self._opened = []
+        self.dist_barrier()                       # peers have unmapped our buffers before they are freed
+        self.views = []
+        for ptr in self.own + [self.own_flags]:
+            self.L.bf_dev_free(ctypes.c_void_p(ptr))
+        self.own, self.own_flags = [], None
 
 
 def assemble_reference(slices, n_directions):

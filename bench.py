@@ -511,12 +511,16 @@ def main():
     from lib.sharded import shard_bounds
     per, d_begin, d_count = shard_bounds(D, world, rank)
     pipe, peer = None, None
+    gather_note = None
     if world > 1 and args.gather == "p2p":
         from lib.sharded import PeerGather
-        peer = PeerGather(D, F, rank, world, dist, depth=int(os.environ.get("BF_GATHER_DEPTH", "2")))   # kernel stores into every rank's buffer
-        d_maps = torch.zeros((F, D), device="cuda")
-        fs, ds = D, 1
-    elif world > 1:
+        try:
+            peer = PeerGather(D, F, rank, world, dist, depth=int(os.environ.get("BF_GATHER_DEPTH", "2")))   # kernel stores into every rank's buffer
+            d_maps = torch.zeros((F, D), device="cuda")
+            fs, ds = D, 1
+        except RuntimeError as e:               # raised on every rank together: fall back to the NCCL route
+            peer, gather_note = None, str(e)
+    if world > 1 and peer is None:
         from lib.sharded import GatherPipeline
         pipe = GatherPipeline(D, F, rank, world, torch.device("cuda"), dist)   # direction-major, gather in place
         d_maps = pipe.bufs[0]
@@ -713,7 +717,7 @@ def main():
                            world, (", all-gather fused into the kernel: epilogue stores go to every rank's buffer over NVLink peer memory"
                             if peer else ", one in-place NCCL all-gather per step on a second stream") if world > 1 else ""),
                        "exact_sum": args.exact_sum},
-            "sum_step_ms": dev_ms, "wall_s": t_wall, "gather_check": gather_check, "gpu_launches": launches, "clocks": clocks,
+            "sum_step_ms": dev_ms, "wall_s": t_wall, "gather_check": gather_check, "gather_note": gather_note, "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "miso": miso, "mvdr": mvdr, "replay": replay, "heatmap": heat, "fir": fir,
         }
         print(json.dumps(line))

@@ -140,32 +140,57 @@ class PeerGather:
             out = vp()
             _native.check(L.bf_dev_alloc(ctypes.c_size_t(nbytes), ctypes.byref(out)))
             return out.value
-        self.own = [alloc(n_buf * 4) for _ in range(depth)]
-        self.own_flags = alloc(8 * 8)
-        handles = []
-        for ptr in self.own + [self.own_flags]:
-            h = (ctypes.c_ubyte * 64)()
-            _native.check(L.bf_ipc_export(vp(ptr), h))
-            handles.append(bytes(h))
+        # Every collective below is reached by every rank whatever fails locally: a failure is carried as
+        # data and raised on all ranks together (the caller can then fall back to the NCCL route).
+        self.own, self.own_flags, self._opened = [], None, []
+        handles, err = None, None
+        try:
+            import os
+            if os.environ.get("BF_PEER_GATHER_DISABLE") == str(rank) or os.environ.get("BF_PEER_GATHER_DISABLE") == "all":
+                raise RuntimeError("disabled by BF_PEER_GATHER_DISABLE (test hook)")
+            self.own = [alloc(n_buf * 4) for _ in range(depth)]
+            self.own_flags = alloc(8 * 8)
+            handles = []
+            for ptr in self.own + [self.own_flags]:
+                h = (ctypes.c_ubyte * 64)()
+                _native.check(L.bf_ipc_export(vp(ptr), h))
+                handles.append(bytes(h))
+        except Exception as e:  # noqa: BLE001
+            handles, err = None, "export: %s" % e
         everyone = [None] * world
         dist.all_gather_object(everyone, handles)
         self.bufs = [[None] * world for _ in range(depth)]      # [depth][rank] device pointers
         self.flags = [None] * world
-        self._opened = []
-        for r in range(world):
-            for k in range(depth + 1):
-                if r == rank:
-                    ptr = (self.own + [self.own_flags])[k]
-                else:
-                    out = vp()
-                    hb = (ctypes.c_ubyte * 64).from_buffer_copy(everyone[r][k])
-                    _native.check(L.bf_ipc_open(hb, ctypes.byref(out)))
-                    ptr = out.value
-                    self._opened.append(ptr)
-                if k < depth:
-                    self.bufs[k][r] = ptr
-                else:
-                    self.flags[r] = ptr
+        if err is None and any(h is None for h in everyone):
+            err = "a peer could not export its buffers"
+        if err is None:
+            try:
+                for r in range(world):
+                    for k in range(depth + 1):
+                        if r == rank:
+                            ptr = (self.own + [self.own_flags])[k]
+                        else:
+                            out = vp()
+                            hb = (ctypes.c_ubyte * 64).from_buffer_copy(everyone[r][k])
+                            _native.check(L.bf_ipc_open(hb, ctypes.byref(out)))
+                            ptr = out.value
+                            self._opened.append(ptr)
+                        if k < depth:
+                            self.bufs[k][r] = ptr
+                        else:
+                            self.flags[r] = ptr
+            except Exception as e:  # noqa: BLE001
+                err = "open: %s" % e
+        errs = [None] * world
+        dist.all_gather_object(errs, err)
+        bad = [(r, e) for r, e in enumerate(errs) if e]
+        if bad:
+            for ptr in self._opened:
+                L.bf_ipc_close(vp(ptr))
+            dist.barrier()
+            for ptr in self.own + ([self.own_flags] if self.own_flags else []):
+                L.bf_dev_free(vp(ptr))
+            raise RuntimeError("PeerGather: peer memory unavailable (rank %d: %s)" % bad[0])
         self._buf_arrays = [(vp * world)(*[vp(x) for x in self.bufs[k]]) for k in range(depth)]
         self._flag_array = (vp * world)(*[vp(x) for x in self.flags])
         self.views = [torch.as_tensor(_DevArray(self.own[k], (world, frames, self.per), "<f4"), device="cuda")

@@ -484,7 +484,23 @@ int bf_mimo_host_batch(int algo, const float *signals, float *images, int frames
     }
     const size_t sig_f = (size_t)S.cfg.n_microphones * S.cfg.n_samples;     // floats per frame
     const int D = S.cfg.max_res_x * S.cfg.max_res_y;
-    const int chunk = frames < 16 ? frames : 16;
+    // chunk schedule: a small first chunk so the first kernel starts early, then chunks of up to 32
+    // frames (fewer partial tile rounds); `chunk` is the largest one (buffer size)
+    std::vector<int> c_start, c_size;
+    {
+        int first = frames / 8;
+        first = first < 4 ? 4 : (first > 16 ? 16 : first);
+        if (first > frames) first = frames;
+        c_start.push_back(0); c_size.push_back(first);
+        for (int f = first; f < frames;) {
+            const int left = frames - f;
+            const int take = left > 48 ? 32 : (left > 32 ? (left + 1) / 2 : left);
+            c_start.push_back(f); c_size.push_back(take);
+            f += take;
+        }
+    }
+    int chunk = 0;
+    for (int v : c_size) chunk = v > chunk ? v : chunk;
     static cudaStream_t st_in = nullptr, st_run = nullptr, st_out = nullptr;
     static cudaEvent_t ev_in[2], ev_run[2], ev_out[2];
     static DevBuf d_sig[2], d_img[2];
@@ -515,15 +531,15 @@ int bf_mimo_host_batch(int algo, const float *signals, float *images, int frames
     }
     if ((rc = upload_mics(adaptive_array, n))) return rc;
     BF_CUDA(cudaStreamSynchronize(0));
-    const int nchunks = (frames + chunk - 1) / chunk;
+    const int nchunks = (int)c_size.size();
     auto drain = [&](int k) -> int {          // wait for chunk k's results, un-stage them
-        const int sl = k & 1, f0 = k * chunk, fc = (frames - f0) < chunk ? (frames - f0) : chunk;
+        const int sl = k & 1, f0 = c_start[k], fc = c_size[k];
         BF_CUDA(cudaEventSynchronize(ev_out[sl]));
         if (!out_pinned) memcpy(images + (size_t)f0 * D, h_out[sl], (size_t)fc * D * sizeof(float));
         return BF_OK;
     };
     for (int k = 0; k < nchunks; k++) {
-        const int sl = k & 1, f0 = k * chunk, fc = (frames - f0) < chunk ? (frames - f0) : chunk;
+        const int sl = k & 1, f0 = c_start[k], fc = c_size[k];
         if (k >= 2 && (rc = drain(k - 2))) return rc;                  // slot sl is free again
         const float *src = signals + (size_t)f0 * sig_f;
         if (!in_pinned) { memcpy(h_in[sl], src, (size_t)fc * sig_f * sizeof(float)); src = (const float *)h_in[sl]; }

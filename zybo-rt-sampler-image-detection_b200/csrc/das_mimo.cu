@@ -26,9 +26,13 @@
 //     (group, microphone), classified as UNIFORM (one delay for all 8 directions),
 //     TWO-RUN (delay changes once inside the group) or GENERAL; each warp copies its
 //     next 32 entries into a private shared-memory slot one chunk ahead and reads
-//     them back with a single broadcast LDS.128 per microphone
+//     them back with broadcast loads two microphones ahead of their use
 //   * for pad the shifted row of microphone m+1 is loaded while microphone m is
 //     being accumulated (software pipeline, two register row buffers)
+//   * GATHER instantiation (direction-sharded multi-GPU runs): the epilogue also stores every
+//     value into the same position of the peer GPUs' buffers (CUDA-IPC mapped, NVLink P2P
+//     stores) and the step flags of that exchange are handled inside the kernel -- the
+//     all-gather is fused into the map kernel
 //   * the epilogue reproduces out/n, square, in-order sum over t, /N exactly
 //     (exact_sum) or uses a warp-shuffle tree
 #include "bf_common.cuh"

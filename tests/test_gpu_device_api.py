@@ -200,7 +200,7 @@ def test_host_batch_replay_equals_per_buffer_calls(algo_name, pinned):
     L.load_coefficients_pad(nat.ptr(whole), whole.size)
     L.load_coefficients_lerp(nat.ptr(d32), d32.size)
     nat.check()
-    F = 37                                            # 16 + 16 + 5: three chunks, ragged tail
+    F = 37                                            # chunk schedule 4 + 17 + 16 (small first chunk, ragged)
     rng = np.random.default_rng(21)
     frames = rng.standard_normal((F, M, N)).astype(np.float32)
     frames[3] = g["signals"]
@@ -220,6 +220,30 @@ def test_host_batch_replay_equals_per_buffer_calls(algo_name, pinned):
         got = np.full((F, D), np.nan, np.float32)
         nat.check(L.bf_mimo_host_batch(algo, nat.ptr(frames), nat.ptr(got), F, nat.ptr(mics), n))
     assert bits_equal(got, single)
+
+
+def test_host_batch_chunk_schedule_any_frame_count():
+    """Every frame count goes through the chunk schedule of bf_mimo_host_batch (small first chunk, then up to
+    32 frames) and still equals one device launch over the same frames."""
+    config, nat, L = _setup("c1")
+    torch = _torch()
+    from lib import directions
+    mics = nat.i32(gold("c1")["mic_ids"])
+    D, n, N, M = 400, 64, 256, 64
+    whole, _ = directions.whole_and_f32()
+    L.load_coefficients_pad(nat.ptr(whole), whole.size)
+    nat.check()
+    rng = np.random.default_rng(5)
+    frames = rng.standard_normal((131, M, N)).astype(np.float32)
+    d_sig, d_mics = torch.from_numpy(frames).cuda(), torch.from_numpy(mics).cuda()
+    d_ref = torch.zeros((131, D), device="cuda")
+    nat.check(L.bf_mimo_dev(nat.ALGO_PAD, d_sig.data_ptr(), d_ref.data_ptr(), 131, d_mics.data_ptr(), n, 0, D, None))
+    torch.cuda.synchronize()
+    ref = d_ref.cpu().numpy()
+    for F in (1, 2, 3, 4, 5, 8, 31, 32, 33, 47, 48, 49, 64, 65, 97, 131):
+        got = np.full((F, D), np.nan, np.float32)
+        nat.check(L.bf_mimo_host_batch(nat.ALGO_PAD, nat.ptr(frames), nat.ptr(got), F, nat.ptr(mics), n))
+        assert bits_equal(got, ref[:F]), F
 
 
 @pytest.mark.parametrize("quirk", [1, 0])

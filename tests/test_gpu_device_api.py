@@ -96,6 +96,51 @@ def test_miso_stream_vs_oracle(algo_name, n_use, blocks):
     assert bits_equal(d_out2.cpu().numpy(), got)
 
 
+@pytest.mark.parametrize("taps", [8, 32])
+@pytest.mark.parametrize("n_use,blocks", [(64, 70), (37, 9)])
+def test_miso_fir_hybrid_stream_vs_oracle(taps, n_use, blocks):
+    """FIR (both accumulation orders) and hybrid MISO streams through the ring kernel == per-sample kernel ==
+    oracle, bit for bit: fused (8 taps) and unfused (32 taps) chains, shuffled microphones, post-scale."""
+    from oracle import cpu
+    torch = _torch()
+    from lib import _native as nat
+    L = nat.lib()
+    M, N, X, Y = 256, 256, 6, 5
+    D = X * Y
+    nat.configure(M, N, taps, X, Y, 128.0)
+    rng = np.random.default_rng(blocks + n_use + taps)
+    sig = rng.standard_normal((blocks, M, N)).astype(np.float32)
+    mics = nat.i32(rng.permutation(M)[:n_use])
+    h = (rng.standard_normal((D, n_use, taps)) / taps).astype(np.float32)
+    d32 = (rng.random((D, n_use)) * 59.5).astype(np.float32)
+    d32[17, :3] = [0.0, 5.0, 254.5]
+    L.load_coefficients_convolve(nat.ptr(h), h.size)
+    L.load_coefficients_convolve_hybrid(nat.ptr(d32), d32.size)
+    nat.check()
+    off = 17 * n_use
+    d_sig, d_mics = torch.from_numpy(sig).cuda(), torch.from_numpy(mics).cuda()
+    # offset units follow the reference: tap-table FLOATS for FIR (d*n*T), entries for hybrid (d*n)
+    for algo, off_a, ref_fn in (
+            (nat.ALGO_FIR_SEQ, off * taps, lambda b: cpu.miso_fir(sig[b], mics, h, off * taps, taps, 0)),
+            (nat.ALGO_FIR_LANES, off * taps, lambda b: cpu.miso_fir(sig[b], mics, h, off * taps, taps, 1)),
+            (nat.ALGO_HYBRID, off, lambda b: cpu.miso_hybrid(sig[b], mics, d32, off, taps))):
+        outs = []
+        for simple in (0, 1):
+            L.bf_set_kernel_options(simple, 1)
+            d_out = torch.full((blocks, N), float("nan"), device="cuda")
+            nat.check(L.bf_miso_dev(algo, d_sig.data_ptr(), d_out.data_ptr(), blocks, d_mics.data_ptr(), n_use, off_a, 0, None))
+            torch.cuda.synchronize()
+            outs.append(d_out.cpu().numpy())
+        L.bf_set_kernel_options(0, 1)
+        assert bits_equal(outs[0], outs[1]), algo
+        for b in (0, blocks // 2, blocks - 1):
+            assert bits_equal(outs[0][b], ref_fn(b)), (algo, b)
+        d_out = torch.zeros((blocks, N), device="cuda")
+        nat.check(L.bf_miso_dev(algo, d_sig.data_ptr(), d_out.data_ptr(), blocks, d_mics.data_ptr(), n_use, off_a, 1, None))
+        torch.cuda.synchronize()
+        assert bits_equal(d_out.cpu().numpy()[1], cpu.miso_scale(ref_fn(1), n_use, 128.0)), algo
+
+
 def test_full_size_c3_properties():
     """BASELINE config C3 (256 mics, 180x180 grid) at full size: golden image from the reference,
     tiled == simple on a slice, permutation/idempotence/scaling properties."""

@@ -33,10 +33,11 @@ off = (14 * 20 + 6) * n
 for name, algo in (("pad", nat.ALGO_PAD), ("lerp", nat.ALGO_LERP), ("fir_seq", nat.ALGO_FIR_SEQ),
                    ("fir_lanes", nat.ALGO_FIR_LANES), ("hybrid", nat.ALGO_HYBRID)):
     ts = []
+    off_a = off * 8 if algo in (nat.ALGO_FIR_SEQ, nat.ALGO_FIR_LANES) else off     # FIR offsets are tap-table floats
     for i in range(5):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        nat.check(L.bf_miso_dev(algo, sig.data_ptr(), out.data_ptr(), blocks, d_mics.data_ptr(), n, off, 1, None))
+        nat.check(L.bf_miso_dev(algo, sig.data_ptr(), out.data_ptr(), blocks, d_mics.data_ptr(), n, off_a, 1, None))
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))

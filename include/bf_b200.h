@@ -229,6 +229,17 @@ int bf_fd_mvdr_timings(float *ms5);
 /* loaded covariance of the last MVDR call: HOST double [bins][M][M][2] */
 int bf_fd_get_covariance(double *cov, size_t count);
 
+/* Wire format of one sample instant (receiver.h:51-59 `msg`): what the Zybo sends per UDP datagram
+ * and what lib/capture.py extracts from pcap / pcapng files.  bf_ingest_dev takes the `stream`
+ * payloads of n_samples consecutive datagrams with this 8-byte header stripped. */
+typedef struct bf_datagram_header {
+    uint16_t frequency;      /* sampling rate, Hz */
+    int8_t n_arrays;         /* 8x8 arrays daisy-chained (1..4) */
+    int8_t protocol_ver;
+    int32_t counter;         /* sample counter: gaps = dropped datagrams */
+    /* int32_t stream[N_MICROPHONES] follows */
+} bf_datagram_header;
+
 /* ---- wire-format ingest (receiver.c:94-151), SURVEY 8f "next" #1 -------------------------
  * d_stream  device int32 [frames][n_samples][n_microphones]: the `stream` payload of
  *           n_samples consecutive datagrams (receiver.h:51-59), header stripped

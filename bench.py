@@ -273,6 +273,29 @@ def mvdr_c4(nat, L, torch, stream, bins=512, dirs=32768, K=64):
                          "peak_source": "measured dense bf16 burst (MEASURED_PEAKS.json); tf32 peaks at half of it"}}
 
 
+def replay_c5_sharded_local(torch, nat, algo, d_mics, n, D, M, N, rank):
+    """C5 across GPUs, this rank's part: its own 20 s recording (recording id = rank, seed 1238 + id) replayed
+    entirely on its GPU (recordings shard with no collective).  Returns (frames, ms); no collective in here."""
+    from lib import replay
+    seconds = 20
+    samples = seconds * 48828
+    gen = torch.Generator(device="cuda").manual_seed(1238 + rank)
+    rec = torch.empty((M, samples), device="cuda")
+    for i in range(0, M, 32):
+        rec[i:i + 32].normal_(generator=gen)
+    rec *= 0.05
+    total = replay.n_frames_in(samples)
+    maps = torch.empty((total, D), device="cuda")
+    replay.replay_dev(algo, rec, d_mics, n, out=maps)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    replay.replay_dev(algo, rec, d_mics, n, out=maps)
+    b.record()
+    torch.cuda.synchronize()
+    return total, a.elapsed_time(b)
+
+
 def replay_c5(args, nat, torch, algo, d_mics, n, D, M, N):
     """BASELINE config C5 on a bounded sample: a 20 s slice of a 256-channel recording resident in
     HBM (1.0 GB, channel-major like PC/record.py's .npy), power-map video at 30 fps: window gather
@@ -679,7 +702,25 @@ def main():
         del h_pool, h_maps
 
         # ---- extra: BASELINE config C5 (bounded sample), then C2 and C4 -----------------------
-        if rank == 0 and args.workload == "c3":
+        if world > 1 and args.workload == "c3":
+            frames_r, ms_r, err_r = 0, 0.0, None
+            try:
+                dist.barrier()
+                frames_r, ms_r = replay_c5_sharded_local(torch, nat, algo, d_mics, n, D, M, N, rank)
+            except Exception as e:  # noqa: BLE001
+                err_r = str(e)
+            tr = torch.tensor([ms_r, float(frames_r), 0.0 if err_r is None else 1.0], device="cuda", dtype=torch.float64)
+            tmax = tr.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)            # slowest rank, any failure
+            dist.all_reduce(tr, op=dist.ReduceOp.SUM)
+            if float(tmax[2]) > 0:
+                replay = {"error": err_r or "a peer rank failed"}
+            else:
+                fps_all = float(tr[1]) / (float(tmax[0]) * 1e-3)
+                replay = {"workload": "C5 sharded: %d recordings of 20 s (one per GPU, 1.0 GB each, resident), 30 fps video, "
+                                      "180x180 maps, %d frames in total, no collective" % (world, int(tr[1])),
+                          "frames_per_s": fps_all, "x_realtime_at_30fps": fps_all / 30.0, "ms": float(tmax[0])}
+        elif rank == 0 and args.workload == "c3":
             try:
                 replay = replay_c5(args, nat, torch, algo, d_mics, n, D, M, N)
             except Exception as e:  # noqa: BLE001

@@ -75,3 +75,24 @@ def test_two_rank_gather_assembles_the_map(tmp_path):
     for r in range(2):
         got = np.load(os.path.join(str(tmp_path), "rank%d.npy" % r))
         assert got.shape == (77, 3) and np.array_equal(got, want)      # every rank holds the full map
+
+
+def test_peer_gather_layout_model():
+    """Layout of the fused kernel + all-gather path (lib.sharded.PeerGather): every rank writes its slice of a
+    [world][F][per] buffer on every rank; assemble_peer_layout turns that into [F][D] maps.  NumPy model of
+    what bf_mimo_dev_gather stores (frame stride per, direction stride 1, origin d_begin, slice offset
+    rank*F*per), for ragged direction counts."""
+    import numpy as np
+    from lib.sharded import assemble_peer_layout, shard_bounds
+    rng = np.random.default_rng(0)
+    for D, world, F in ((400, 2, 3), (32400, 8, 2), (91, 4, 5), (7, 8, 1)):
+        maps = rng.standard_normal((F, D)).astype(np.float32)
+        per = shard_bounds(D, world, 0)[0]
+        buf = np.zeros((world, F, per), np.float32)
+        flat = buf.reshape(-1)
+        for rank in range(world):
+            _, d_begin, d_count = shard_bounds(D, world, rank)
+            for f in range(F):
+                for d in range(d_begin, d_begin + d_count):
+                    flat[rank * F * per + f * per + (d - d_begin)] = maps[f, d]      # what the epilogue stores
+        assert np.array_equal(assemble_peer_layout(buf, D), maps)

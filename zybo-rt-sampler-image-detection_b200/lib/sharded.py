@@ -227,8 +227,7 @@ class PeerGather:
 
     def maps(self, i):
         """[F][D] tensor of step i (a copy: the gather layout is [rank][F][per]); waits for the step."""
-        v = self.ready(i)
-        return v.permute(1, 0, 2).reshape(self.F, self.world * self.per)[:, :self.D]
+        return assemble_peer_layout(self.ready(i), self.D)
 
     def check(self):
         if int(self.timed_out.item()):
@@ -245,6 +244,15 @@ class PeerGather:
         for ptr in self.own + [self.own_flags]:
             self.L.bf_dev_free(ctypes.c_void_p(ptr))
         self.own, self.own_flags = [], None
+
+
+def assemble_peer_layout(buf, n_directions):
+    """Gather-buffer layout of the fused path, [world][F][per] (slice r = rank r's directions), to maps
+    [F][D].  Works on NumPy arrays and torch tensors alike."""
+    world, F, per = buf.shape
+    if hasattr(buf, "permute"):
+        return buf.permute(1, 0, 2).reshape(F, world * per)[:, :n_directions]
+    return buf.transpose(1, 0, 2).reshape(F, world * per)[:, :n_directions]
 
 
 def assemble_reference(slices, n_directions):

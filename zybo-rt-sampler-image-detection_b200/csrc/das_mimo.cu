@@ -408,11 +408,16 @@ __global__ void __launch_bounds__((max_warps(LERP) + 1) * 32, 1) das_mimo_kernel
                     if (mm < cnt) process_mic<J, LERP, PACK, true>(acc, e0, ebuf + mm, rowp, row_bytes, A, nullptr);
                 } else {
                     float2 A[J / 2];
-                    uint2 en = e2p[0];
-                    for (int mm = 0; mm < cnt; mm++, rowp += mic_bytes) {
-                        const uint2 e = en;
-                        en = e2p[2 * (mm + 1)];                   // next entry in flight during this microphone
-                        process_mic<J, LERP, PACK, false>(acc, e, ebuf + mm, rowp, row_bytes, A, wbuf + mm * 8);
+                    if (LERP) {
+                        uint2 en = e2p[0];
+                        for (int mm = 0; mm < cnt; mm++, rowp += mic_bytes) {
+                            const uint2 e = en;
+                            en = e2p[2 * (mm + 1)];               // next entry in flight during this microphone
+                            process_mic<J, LERP, PACK, false>(acc, e, ebuf + mm, rowp, row_bytes, A, wbuf + mm * 8);
+                        }
+                    } else {
+                        for (int mm = 0; mm < cnt; mm++, rowp += mic_bytes)
+                            process_mic<J, LERP, PACK, false>(acc, e2p[2 * mm], ebuf + mm, rowp, row_bytes, A, nullptr);
                     }
                 }
             }

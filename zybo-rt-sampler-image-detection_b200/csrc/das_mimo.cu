@@ -47,7 +47,10 @@ static constexpr int kStages = 4;      // smem ring depth
 // buffers and eight weights do not fit 96 without spilling into the add loop).
 static constexpr int kMaxWarpsPad = 19, kMaxWarpsLerp = 15;
 __host__ __device__ constexpr int max_warps(bool lerp) { return lerp ? kMaxWarpsLerp : kMaxWarpsPad; }
-static constexpr int kScratchStride = 68;
+static constexpr int kScratchStride = 36;   // floats per direction row of the epilogue scratch (32 + pad)
+// per-warp shared slot = two buffers; a buffer holds the staged entries of one chunk (uint4[32], + float[32][8]
+// weights for lerp) and doubles as the epilogue scratch (8 rows x 36 floats) once its chunk is consumed
+__host__ __device__ constexpr int slot_buf_bytes(bool lerp) { return lerp ? 1536 : 1152; }
 
 enum { kGeneral = 0u, kUniform = 1u, kTwoRun = 2u };
 
@@ -330,33 +333,30 @@ __global__ void __launch_bounds__((max_warps(LERP) + 1) * 32, 1) das_mimo_kernel
     }
 
     // ======================= consumer warps =================================
-    // per-warp shared slot: epilogue scratch, reused during the main loop as the
-    // entry buffer (uint4[32]) and, for lerp, the weight buffer (float[32][8])
-    float *scratch = scratch_all + warp * (kR * kScratchStride);
-    uint4 *ebuf = (uint4 *)scratch;
-    float *wbuf = scratch + 128;
+    // per-warp shared slot: two buffers (see slot_buf_bytes).  Entries (and lerp weights) of the next chunk
+    // are copied global -> shared with cp.async while the current chunk is processed: no registers held.
+    constexpr int BUF = slot_buf_bytes(LERP);
+    unsigned char *slot = (unsigned char *)scratch_all + (size_t)warp * 2 * BUF;
 
     auto group_of = [&](int tile) {
         const int frame = tile / p.tiles_per_frame;
         return (tile - frame * p.tiles_per_frame) * W + warp;
     };
-    // entries of chunk c of `tile` for this lane (one chunk ahead of their use)
-    uint4 e_pref = make_uint4(kUniform, 0u, 0u, 0u);
-    float4 w_pref0 = make_float4(0.f, 0.f, 0.f, 0.f), w_pref1 = w_pref0;
-    auto prefetch_entries = [&](int tile, int c) {
+    auto prefetch_entries = [&](int tile, int c, unsigned char *dst) {
         if (tile >= p.total_tiles) return;
         const int g = group_of(tile);
         if (g >= p.groups) return;
         const int m = min(c * p.Mt + lane, p.n - 1);
         const size_t idx = (size_t)g * p.n + m;
-        e_pref = __ldg(p.offs + idx);
+        bfptx::cp_async16(dst + lane * 16, p.offs + idx);
         if (LERP) {
-            const float4 *wp = (const float4 *)(p.wts + idx * kR);
-            w_pref0 = __ldg(wp);
-            w_pref1 = __ldg(wp + 1);
+            const float *wp = p.wts + idx * kR;
+            bfptx::cp_async16(dst + 512 + lane * 32, wp);
+            bfptx::cp_async16(dst + 512 + lane * 32 + 16, wp + 4);
         }
     };
-    prefetch_entries(blockIdx.x, 0);
+    uint32_t qc = 0;                                      // running chunk counter: buffer = qc & 1
+    prefetch_entries(blockIdx.x, 0, slot);
 
     int s = 0;
     uint32_t ph = 0;
@@ -374,16 +374,14 @@ __global__ void __launch_bounds__((max_warps(LERP) + 1) * 32, 1) das_mimo_kernel
 
         for (int c = 0; c < nchunks; c++) {
             const int cnt = min(p.Mt, p.n - c * p.Mt);
-            if (active) {
-                ebuf[lane] = e_pref;
-                if (LERP) {
-                    *(float4 *)(wbuf + lane * 8) = w_pref0;
-                    *(float4 *)(wbuf + lane * 8 + 4) = w_pref1;
-                }
-            }
+            unsigned char *cur = slot + (qc & 1u) * BUF;
+            const uint4 *ebuf = (const uint4 *)cur;
+            const float *wbuf = (const float *)(cur + 512);
+            bfptx::cp_async_wait_all();
             __syncwarp();
-            if (c + 1 < nchunks) prefetch_entries(tile, c + 1);
-            else prefetch_entries(tile + gridDim.x, 0);
+            if (c + 1 < nchunks) prefetch_entries(tile, c + 1, slot + ((qc + 1u) & 1u) * BUF);
+            else prefetch_entries(tile + gridDim.x, 0, slot + ((qc + 1u) & 1u) * BUF);
+            qc++;
             bfptx::mbar_wait(&full[s], ph);
             if (active) {
                 const char *rowp = (const char *)(stages + (size_t)s * stage_bytes) + lane * 4;
@@ -448,22 +446,23 @@ __global__ void __launch_bounds__((max_warps(LERP) + 1) * 32, 1) das_mimo_kernel
         const int valid = min(kR, p.d_count - g * kR);
         const long ds = p.img_ds;
         if (EXACT) {
+            // the buffer of the chunk just consumed is free; the other one holds the next tile's first entries
+            float *scratch = (float *)(slot + ((qc - 1u) & 1u) * BUF);
             float run = 0.0f;
 #pragma unroll
-            for (int q = 0; q < J / 2; q++) {
+            for (int q = 0; q < J; q++) {                 // 32 samples per round: t = 32 q + lane
 #pragma unroll
                 for (int r = 0; r < kR; r++) {
-                    float x0 = acc[r][q].x, x1 = acc[r][q].y;
-                    if (p.n_pow2) { x0 = __fmul_rn(x0, p.inv_n); x1 = __fmul_rn(x1, p.inv_n); }
-                    else          { x0 = __fdiv_rn(x0, p.fn);    x1 = __fdiv_rn(x1, p.fn); }
+                    float x0 = (q & 1) ? acc[r][q >> 1].y : acc[r][q >> 1].x;
+                    if (p.n_pow2) x0 = __fmul_rn(x0, p.inv_n);
+                    else          x0 = __fdiv_rn(x0, p.fn);
                     scratch[r * kScratchStride + lane] = __fmul_rn(x0, x0);
-                    scratch[r * kScratchStride + 32 + lane] = __fmul_rn(x1, x1);
                 }
                 __syncwarp();
                 if (lane < kR) {
                     const float4 *s4 = (const float4 *)(scratch + lane * kScratchStride);
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
+                    for (int i = 0; i < 8; i++) {
                         const float4 v = s4[i];
                         run = __fadd_rn(run, v.x);
                         run = __fadd_rn(run, v.y);
@@ -625,7 +624,7 @@ int mimo_tiled(int algo, const float *d_sig, float *d_img, int frames, const int
 
     // stage geometry: as many mic rows per stage as fit in the smem budget (<= 32: one entry per lane)
     const size_t row_bytes = (size_t)(P + N) * 4 * (lerp ? 2 : 1);
-    const size_t scratch_bytes = (size_t)W * kR * kScratchStride * 4;
+    const size_t scratch_bytes = (size_t)W * 2 * slot_buf_bytes(lerp);
     const size_t budget = 227 * 1024 - 256 - scratch_bytes - 1024;
     int Mt = 32;
     while (Mt > 1 && (size_t)Mt * row_bytes * kStages > budget) Mt >>= 1;

@@ -7,7 +7,7 @@
 //   img[d] = 1/N * sum_t ( 1/n * sum_m  delayed_m,d[t] )^2
 //
 // Design (B200 / sm_100a):
-//   * persistent grid, one CTA per SM; a CTA = 1 producer warp + W consumer warps
+//   * persistent grid, one CTA per SM; a CTA = 1 producer warp + W consumer warps (W <= 19 pad, 15 lerp)
 //   * a consumer warp owns a GROUP of R = 8 consecutive directions and all N
 //     samples of them in registers (lane l holds samples l, l+32, ...), so the
 //     microphone sum runs in the reference's order (m = 0..n-1, fp32) and the
@@ -24,11 +24,13 @@
 //     only reaches half the FP32 rate on this SM, measured)
 //   * the table is re-laid out once per load into 16-byte "group entries" per
 //     (group, microphone), classified as UNIFORM (one delay for all 8 directions),
-//     TWO-RUN (delay changes once inside the group) or GENERAL; each warp copies its
-//     next 32 entries into a private shared-memory slot one chunk ahead and reads
-//     them back with broadcast loads two microphones ahead of their use
-//   * for pad the shifted row of microphone m+1 is loaded while microphone m is
-//     being accumulated (software pipeline, two register row buffers)
+//     TWO-RUN (delay changes once inside the group) or GENERAL; the next chunk's 32
+//     entries (and lerp weights) of a warp arrive in its private, double-buffered
+//     shared-memory slot by cp.async while the current chunk is processed
+//   * latency is hidden by warps, not registers: pad runs 19 consumer warps at 96
+//     registers (five per scheduler) without a register row prefetch -- measured
+//     faster than 15 warps at 128 registers with one (profiles/r1_kernel_variants.md);
+//     the PIPE code path (row prefetch) is kept but compiled out
 //   * GATHER instantiation (direction-sharded multi-GPU runs): the epilogue also stores every
 //     value into the same position of the peer GPUs' buffers (CUDA-IPC mapped, NVLink P2P
 //     stores) and the step flags of that exchange are handled inside the kernel -- the

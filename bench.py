@@ -454,7 +454,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--algo", default="pad", choices=["pad", "lerp"])
-    ap.add_argument("--frames", type=int, default=64, help="maps per step")
+    ap.add_argument("--frames", type=int, default=128, help="maps per step")
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the MISO / e2e extras")

@@ -207,6 +207,77 @@ __device__ __forceinline__ void two_run(float2 (&acc)[kR][J / 2], const float2 (
                                 : das_accum<LERP, PACK>(acc[r][q], a2[q], d2[q], h[r]);
 }
 
+// Sample-pair-outer form of one microphone (used by the shipped loops): only the two row values (and, for
+// lerp, the two differences) of ONE sample pair are live at a time instead of a whole row, which is what
+// lets the kernel run at 96 registers.  Same arithmetic per accumulator as process_mic.
+template <int J>
+__device__ __forceinline__ float2 ld_pair(const char *p, int q)
+{
+    return make_float2(*(const float *)(p + q * 256), *(const float *)(p + q * 256 + 128));
+}
+
+template <int J, bool LERP, bool PACK, int S>
+__device__ __forceinline__ void mic_pairs(float2 (&acc)[kR][J / 2], const char *pa, const char *pb,
+                                          const uint32_t row_bytes, const float (&h)[kR])
+{
+#pragma unroll
+    for (int q = 0; q < J / 2; q++) {
+        const float2 a = ld_pair<J>(pa, q);
+        const float2 d = LERP ? ld_pair<J>(pa + row_bytes, q) : a;
+        float2 a2 = a, d2 = d;
+        if (S < kR) {
+            a2 = ld_pair<J>(pb, q);
+            d2 = LERP ? ld_pair<J>(pb + row_bytes, q) : a2;
+        }
+#pragma unroll
+        for (int r = 0; r < kR; r++)
+            acc[r][q] = (r < S) ? das_accum<LERP, PACK>(acc[r][q], a, d, h[r])
+                                : das_accum<LERP, PACK>(acc[r][q], a2, d2, h[r]);
+    }
+}
+
+template <int J, bool LERP, bool PACK>
+__device__ __forceinline__ void process_mic_q(float2 (&acc)[kR][J / 2], const uint2 e, const uint4 *efull,
+                                              const char *rowp, const uint32_t row_bytes, const float *wrow)
+{
+    const uint32_t kind = e.x & 3u;
+    const char *pa = rowp + (e.x & 0xfffcu);
+    float h[kR] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (LERP) {
+        const float4 h0 = *(const float4 *)wrow, h1 = *(const float4 *)(wrow + 4);
+        h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w;
+        h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
+    }
+    if (kind == kUniform) {
+        mic_pairs<J, LERP, PACK, kR>(acc, pa, pa, row_bytes, h);
+    } else if (kind == kTwoRun) {
+        const char *pb = rowp + (e.x >> 16);
+        switch (e.y) {
+            case 1: mic_pairs<J, LERP, PACK, 1>(acc, pa, pb, row_bytes, h); break;
+            case 2: mic_pairs<J, LERP, PACK, 2>(acc, pa, pb, row_bytes, h); break;
+            case 3: mic_pairs<J, LERP, PACK, 3>(acc, pa, pb, row_bytes, h); break;
+            case 4: mic_pairs<J, LERP, PACK, 4>(acc, pa, pb, row_bytes, h); break;
+            case 5: mic_pairs<J, LERP, PACK, 5>(acc, pa, pb, row_bytes, h); break;
+            case 6: mic_pairs<J, LERP, PACK, 6>(acc, pa, pb, row_bytes, h); break;
+            default: mic_pairs<J, LERP, PACK, 7>(acc, pa, pb, row_bytes, h); break;
+        }
+    } else {
+        // general (0.4 % of the C3 table): one direction at a time
+        const uint4 ef = *efull;
+#pragma unroll
+        for (int r = 0; r < kR; r++) {
+            const uint32_t wd = (r >> 1) == 0 ? ef.x : ((r >> 1) == 1 ? ef.y : ((r >> 1) == 2 ? ef.z : ef.w));
+            const char *pr = rowp + ((r & 1) ? (wd >> 16) : (wd & 0xfffcu));
+#pragma unroll
+            for (int q = 0; q < J / 2; q++) {
+                const float2 a = ld_pair<J>(pr, q);
+                const float2 d = LERP ? ld_pair<J>(pr + row_bytes, q) : a;
+                acc[r][q] = das_accum<LERP, PACK>(acc[r][q], a, d, h[r]);
+            }
+        }
+    }
+}
+
 // One microphone into the 8 accumulators of the group.  `a` holds the row at the
 // entry's first offset when PRE (prefetched by the caller), else it is loaded here.
 template <int J, bool LERP, bool PACK, bool PRE>
@@ -407,18 +478,8 @@ __global__ void __launch_bounds__((max_warps(LERP) + 1) * 32, 1) das_mimo_kernel
                     }
                     if (mm < cnt) process_mic<J, LERP, PACK, true>(acc, e0, ebuf + mm, rowp, row_bytes, A, nullptr);
                 } else {
-                    float2 A[J / 2];
-                    if (LERP) {
-                        uint2 en = e2p[0];
-                        for (int mm = 0; mm < cnt; mm++, rowp += mic_bytes) {
-                            const uint2 e = en;
-                            en = e2p[2 * (mm + 1)];               // next entry in flight during this microphone
-                            process_mic<J, LERP, PACK, false>(acc, e, ebuf + mm, rowp, row_bytes, A, wbuf + mm * 8);
-                        }
-                    } else {
-                        for (int mm = 0; mm < cnt; mm++, rowp += mic_bytes)
-                            process_mic<J, LERP, PACK, false>(acc, e2p[2 * mm], ebuf + mm, rowp, row_bytes, A, nullptr);
-                    }
+                    for (int mm = 0; mm < cnt; mm++, rowp += mic_bytes)
+                        process_mic_q<J, LERP, PACK>(acc, e2p[2 * mm], ebuf + mm, rowp, (uint32_t)row_bytes, wbuf + mm * 8);
                 }
             }
             __syncwarp();

@@ -29,8 +29,9 @@
 //     shared-memory slot by cp.async while the current chunk is processed
 //   * latency is hidden by warps, not registers: pad runs 19 consumer warps at 96
 //     registers (five per scheduler) without a register row prefetch -- measured
-//     faster than 15 warps at 128 registers with one (profiles/r1_kernel_variants.md);
-//     the PIPE code path (row prefetch) is kept but compiled out
+//     faster than 15 warps at 128 registers with one (profiles/r1_kernel_variants.md; the
+//     prefetching loop is in the git history); a microphone is processed sample-pair-outer,
+//     so only two row values are live next to the 64 accumulators
 //   * GATHER instantiation (direction-sharded multi-GPU runs): the epilogue also stores every
 //     value into the same position of the peer GPUs' buffers (CUDA-IPC mapped, NVLink P2P
 //     stores) and the step flags of that exchange are handled inside the kernel -- the
@@ -168,16 +169,6 @@ struct MimoParams {
     float fn, inv_n;
 };
 
-template <int J>
-__device__ __forceinline__ void load_row(const char *p, float2 (&v)[J / 2])
-{
-#pragma unroll
-    for (int q = 0; q < J / 2; q++) {
-        v[q].x = *(const float *)(p + q * 256);
-        v[q].y = *(const float *)(p + q * 256 + 128);
-    }
-}
-
 // acc += a            (pad:  pad_and_sum.c:45)
 // acc += fma(h, b, a) (lerp: lerp_and_sum.c:54, b = s[i+1]-s[i]); PACK selects the packed
 // add.f32x2 / fma.f32x2 forms -- same IEEE rounding per element either way.
@@ -192,19 +183,6 @@ __device__ __forceinline__ float2 das_accum(float2 acc, float2 a, float2 b, floa
         return make_float2(__fadd_rn(acc.x, __fmaf_rn(h, b.x, a.x)),
                            __fadd_rn(acc.y, __fmaf_rn(h, b.y, a.y)));
     return make_float2(__fadd_rn(acc.x, a.x), __fadd_rn(acc.y, a.y));
-}
-
-template <int J, bool LERP, bool PACK, int S>
-__device__ __forceinline__ void two_run(float2 (&acc)[kR][J / 2], const float2 (&a)[J / 2],
-                                        const float2 (&d)[J / 2], const float2 (&a2)[J / 2],
-                                        const float2 (&d2)[J / 2], const float (&h)[kR])
-{
-#pragma unroll
-    for (int r = 0; r < kR; r++)
-#pragma unroll
-        for (int q = 0; q < J / 2; q++)
-            acc[r][q] = (r < S) ? das_accum<LERP, PACK>(acc[r][q], a[q], d[q], h[r])
-                                : das_accum<LERP, PACK>(acc[r][q], a2[q], d2[q], h[r]);
 }
 
 // Sample-pair-outer form of one microphone (used by the shipped loops): only the two row values (and, for
@@ -278,69 +256,10 @@ __device__ __forceinline__ void process_mic_q(float2 (&acc)[kR][J / 2], const ui
     }
 }
 
-// One microphone into the 8 accumulators of the group.  `a` holds the row at the
-// entry's first offset when PRE (prefetched by the caller), else it is loaded here.
-template <int J, bool LERP, bool PACK, bool PRE>
-__device__ __forceinline__ void process_mic(float2 (&acc)[kR][J / 2], const uint2 e, const uint4 *efull,
-                                            const char *rowp, const size_t row_bytes,
-                                            float2 (&a)[J / 2], const float *wrow)
-{
-    const uint32_t kind = e.x & 3u;
-    const uint32_t oa = e.x & 0xfffcu;
-    float2 d[J / 2];
-    float h[kR];
-    if (!PRE) load_row<J>(rowp + oa, a);
-    if (LERP) {
-        load_row<J>(rowp + row_bytes + oa, d);
-        const float4 h0 = *(const float4 *)wrow, h1 = *(const float4 *)(wrow + 4);
-        h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w;
-        h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
-    }
-    if (kind == kUniform) {
-#pragma unroll
-        for (int r = 0; r < kR; r++)
-#pragma unroll
-            for (int q = 0; q < J / 2; q++)
-                acc[r][q] = das_accum<LERP, PACK>(acc[r][q], a[q], d[q], h[r]);
-    } else if (kind == kTwoRun) {
-        const uint32_t ob = e.x >> 16;
-        float2 a2[J / 2], d2[J / 2];
-        load_row<J>(rowp + ob, a2);
-        if (LERP) load_row<J>(rowp + row_bytes + ob, d2);
-        switch (e.y) {
-            case 1: two_run<J, LERP, PACK, 1>(acc, a, d, a2, d2, h); break;
-            case 2: two_run<J, LERP, PACK, 2>(acc, a, d, a2, d2, h); break;
-            case 3: two_run<J, LERP, PACK, 3>(acc, a, d, a2, d2, h); break;
-            case 4: two_run<J, LERP, PACK, 4>(acc, a, d, a2, d2, h); break;
-            case 5: two_run<J, LERP, PACK, 5>(acc, a, d, a2, d2, h); break;
-            case 6: two_run<J, LERP, PACK, 6>(acc, a, d, a2, d2, h); break;
-            default: two_run<J, LERP, PACK, 7>(acc, a, d, a2, d2, h); break;
-        }
-    } else {
-        // general: reload only when the delay changes from one direction to the next
-        const uint4 ef = *efull;
-        const uint32_t ow[4] = {ef.x, ef.y, ef.z, ef.w};
-        uint32_t prev = oa;
-#pragma unroll
-        for (int r = 0; r < kR; r++) {
-            const uint32_t o = (r & 1) ? (ow[r >> 1] >> 16) : (ow[r >> 1] & 0xfffcu);
-            if (o != prev) {
-                load_row<J>(rowp + o, a);
-                if (LERP) load_row<J>(rowp + row_bytes + o, d);
-                prev = o;
-            }
-#pragma unroll
-            for (int q = 0; q < J / 2; q++)
-                acc[r][q] = das_accum<LERP, PACK>(acc[r][q], a[q], d[q], h[r]);
-        }
-    }
-}
-
 template <int J, bool LERP, bool EXACT, bool PACK, bool GATHER>
 __global__ void __launch_bounds__((max_warps(LERP) + 1) * 32, 1) das_mimo_kernel(const MimoParams p)
 {
     constexpr int N = J * 32;
-    constexpr bool PIPE = false;                         // register row prefetch: off (see max_warps)
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = p.W;
@@ -459,25 +378,7 @@ __global__ void __launch_bounds__((max_warps(LERP) + 1) * 32, 1) das_mimo_kernel
             if (active) {
                 const char *rowp = (const char *)(stages + (size_t)s * stage_bytes) + lane * 4;
                 const uint2 *e2p = (const uint2 *)ebuf;          // first two words of entry i at e2p[2 * i]
-                if (PIPE) {
-                    // rows are loaded one microphone ahead, entries two ahead (an entry is needed for the
-                    // next row's address long before its own adds start)
-                    float2 A[J / 2], B[J / 2];
-                    uint2 e0 = e2p[0], e1 = e2p[2];
-                    load_row<J>(rowp + (e0.x & 0xfffcu), A);
-                    int mm = 0;
-                    for (; mm + 1 < cnt; mm += 2) {
-                        load_row<J>(rowp + mic_bytes + (e1.x & 0xfffcu), B);
-                        const uint2 ea = e2p[2 * (mm + 2)];       // may run one or two entries past cnt: unused then
-                        process_mic<J, LERP, PACK, true>(acc, e0, ebuf + mm, rowp, row_bytes, A, nullptr);
-                        if (mm + 2 < cnt) load_row<J>(rowp + 2 * mic_bytes + (ea.x & 0xfffcu), A);
-                        const uint2 eb = e2p[2 * (mm + 3)];
-                        process_mic<J, LERP, PACK, true>(acc, e1, ebuf + mm + 1, rowp + mic_bytes, row_bytes, B, nullptr);
-                        e0 = ea; e1 = eb;
-                        rowp += 2 * mic_bytes;
-                    }
-                    if (mm < cnt) process_mic<J, LERP, PACK, true>(acc, e0, ebuf + mm, rowp, row_bytes, A, nullptr);
-                } else {
+                {
                     for (int mm = 0; mm < cnt; mm++, rowp += mic_bytes)
                         process_mic_q<J, LERP, PACK>(acc, e2p[2 * mm], ebuf + mm, rowp, (uint32_t)row_bytes, wbuf + mm * 8);
                 }

@@ -46,8 +46,8 @@ static constexpr int kR = 8;           // directions per warp
 static constexpr int kStages = 4;      // smem ring depth
 // Consumer warps per CTA (+1 producer).  pad: 19 + 1 = 640 threads at 96 registers -- five warps per
 // scheduler hide the per-microphone latencies better than a register-hungry row prefetch does with four
-// (measured: 10 302 vs 10 022 maps/s); lerp keeps 15 + 1 = 512 threads at 128 registers (its two row
-// buffers and eight weights do not fit 96 without spilling into the add loop).
+// (measured: 10 302 vs 10 022 maps/s); lerp keeps 15 + 1 = 512 threads at 128 registers (measured: 5 772
+// vs 5 008 maps/s with 19 + 1 at 96).
 static constexpr int kMaxWarpsPad = 19, kMaxWarpsLerp = 15;
 __host__ __device__ constexpr int max_warps(bool lerp) { return lerp ? kMaxWarpsLerp : kMaxWarpsPad; }
 static constexpr int kScratchStride = 36;   // floats per direction row of the epilogue scratch (32 + pad)
@@ -187,7 +187,8 @@ __device__ __forceinline__ float2 das_accum(float2 acc, float2 a, float2 b, floa
 
 // Sample-pair-outer form of one microphone (used by the shipped loops): only the two row values (and, for
 // lerp, the two differences) of ONE sample pair are live at a time instead of a whole row, which is what
-// lets the kernel run at 96 registers.  Same arithmetic per accumulator as process_mic.
+// lets the kernel run at 96 registers: acc[r][q] += row value (pad) or fma(h[r], diff, row value) (lerp),
+// microphones in table order, so every accumulator sees the reference's sequence of roundings.
 template <int J>
 __device__ __forceinline__ float2 ld_pair(const char *p, int q)
 {

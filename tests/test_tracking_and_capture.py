@@ -99,6 +99,26 @@ def test_capture_reader(tmp_path, fmt):
     assert blocks.shape == (2, 256, M) and np.array_equal(blocks[1], streams[256:512])
 
 
+@pytest.mark.parametrize("fmt", ["pcap", "pcapng"])
+def test_capture_streaming_iterator(tmp_path, fmt):
+    from lib import capture
+    rng = np.random.default_rng(8)
+    M, N, P = 64, 32, 32 * 7 + 5                                   # 7 whole blocks + a partial one
+    streams = rng.integers(-1000, 1000, (P, M), dtype=np.int32)
+    frames = [_udp_frame(_datagram(i, streams[i], n_arrays=1)) for i in range(P)]
+    frames.insert(40, _udp_frame(b"x" * 100))
+    ts = 5.0 + np.arange(len(frames)) * 1e-4
+    path = str(tmp_path / ("s." + fmt))
+    (_write_pcap if fmt == "pcap" else _write_pcapng)(path, frames, ts)
+    chunks = list(capture.iter_capture_blocks(path, n_microphones=M, n_samples=N, chunk_blocks=3))
+    assert [c[0].shape[0] for c in chunks] == [3, 3, 1]
+    got = np.concatenate([c[0].reshape(-1, M) for c in chunks])
+    assert np.array_equal(got, streams[:7 * N])
+    assert np.array_equal(np.concatenate([c[1] for c in chunks]), np.arange(7 * N))
+    whole = capture.read_capture(path, n_microphones=M)
+    assert np.array_equal(capture.blocks(whole.stream, N), got.reshape(7, N, M))
+
+
 def test_capture_detects_drops(tmp_path):
     from lib import capture
     M = 64

@@ -122,6 +122,38 @@ def read_capture(path, n_microphones=256):
     return Capture(np.ascontiguousarray(np.stack(rows)), counter, np.array(stamps), hdr[0], hdr[1], hdr[2], dropped)
 
 
+def iter_capture_blocks(path, n_microphones=256, n_samples=256, chunk_blocks=64):
+    """Stream a capture that does not fit in memory (1 h of the 256-channel stream is ~180 GB): memory-map the
+    file and yield (stream int32 [k][n_samples][n_microphones], counter int64 [k*n_samples], timestamps) for
+    successive chunks of up to `chunk_blocks` whole blocks; the tail that does not fill a block is dropped,
+    like the reference's receiver drops a partial buffer.  Each chunk is what replay.signals_from_capture /
+    bf_ingest_dev take."""
+    import mmap
+    size = 8 + 4 * n_microphones
+    with open(path, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as buf:
+        it = _iter_pcapng(buf) if buf[:4] == b"\x0a\x0d\x0d\x0a" else _iter_pcap(buf)
+        want = chunk_blocks * n_samples
+        rows = np.empty((want, n_microphones), np.int32)
+        counters = np.empty(want, np.int64)
+        stamps = np.empty(want, np.float64)
+        fill = 0
+        for ts, frame, link in it:
+            pl = _udp_payload(frame, link)
+            if pl is None or len(pl) != size:
+                continue
+            rows[fill] = np.frombuffer(pl, "<i4", n_microphones, 8)
+            counters[fill] = _HDR.unpack_from(pl)[3]
+            stamps[fill] = ts
+            fill += 1
+            if fill == want:
+                yield rows.reshape(chunk_blocks, n_samples, n_microphones).copy(), counters.copy(), stamps.copy()
+                fill = 0
+        k = fill // n_samples
+        if k:
+            yield (rows[:k * n_samples].reshape(k, n_samples, n_microphones).copy(), counters[:k * n_samples].copy(),
+                   stamps[:k * n_samples].copy())
+
+
 def read_timestamps(csv_path):
     """Second column of the reference's timestamp CSVs (header row, then index,timestamp)."""
     return np.atleast_1d(np.loadtxt(csv_path, delimiter=",", skiprows=1, usecols=1, dtype=np.float64))

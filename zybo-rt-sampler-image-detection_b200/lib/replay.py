@@ -70,21 +70,31 @@ def video_dev(algo, d_recording, d_mic_ids, n, window=(640, 360), fps=30, fs=488
     return {"frames": mine, "maps": maps, "info": info, "confidence": conf, "heat": heat if keep_heat else None}
 
 
-def signals_from_capture(cap, quirk=True, zero_mask=None, norm=16777216.0, rows=8, cols=8):
-    """Packet capture (lib.capture.read_capture) -> device sample buffers: every whole block of
-    N_SAMPLES datagrams becomes one float32 [N_MICROPHONES][N_SAMPLES] frame (the reference's receiver,
-    receiver.c:94-151, on the device).  Returns a torch CUDA tensor [blocks][N_MICROPHONES][N_SAMPLES]."""
+def signals_from_blocks(blocks, n_arrays, quirk=True, zero_mask=None, norm=16777216.0, rows=8, cols=8):
+    """int32 datagram payloads [k][N_SAMPLES][N_MICROPHONES] (lib.capture.blocks / iter_capture_blocks) ->
+    device sample buffers float32 [k][N_MICROPHONES][N_SAMPLES]: the reference's receiver
+    (receiver.c:94-151) on the device."""
     import torch
-    from . import capture
     L = _native.lib()
     M, N = config.N_MICROPHONES, config.N_SAMPLES
-    blk = capture.blocks(cap.stream, N)
-    if blk.shape[2] != M:
-        raise ValueError("capture has %d channels per datagram, config.N_MICROPHONES is %d" % (blk.shape[2], M))
-    d_in = torch.from_numpy(np.ascontiguousarray(blk)).cuda()
-    d_out = torch.zeros((blk.shape[0], M, N), dtype=torch.float32, device="cuda")
+    if blocks.ndim != 3 or blocks.shape[1] != N or blocks.shape[2] != M:
+        raise ValueError("payload blocks are %s, expected (k, N_SAMPLES=%d, N_MICROPHONES=%d)" % (blocks.shape, N, M))
+    d_in = torch.from_numpy(np.ascontiguousarray(blocks, np.int32)).cuda()
+    d_out = torch.zeros((blocks.shape[0], M, N), dtype=torch.float32, device="cuda")
     d_mask = torch.from_numpy(np.ascontiguousarray(zero_mask, np.uint8)).cuda() if zero_mask is not None else None
-    _native.check(L.bf_ingest_dev(d_in.data_ptr(), d_out.data_ptr(), blk.shape[0], int(cap.n_arrays), rows, cols,
+    _native.check(L.bf_ingest_dev(d_in.data_ptr(), d_out.data_ptr(), blocks.shape[0], int(n_arrays), rows, cols,
                                   float(norm), int(bool(quirk)), d_mask.data_ptr() if d_mask is not None else None,
                                   torch.cuda.current_stream().cuda_stream))
     return d_out
+
+
+def signals_from_capture(cap, quirk=True, zero_mask=None, norm=16777216.0, rows=8, cols=8):
+    """Packet capture (lib.capture.read_capture) -> device sample buffers: every whole block of N_SAMPLES
+    datagrams becomes one float32 [N_MICROPHONES][N_SAMPLES] frame.  Returns a torch CUDA tensor
+    [blocks][N_MICROPHONES][N_SAMPLES]."""
+    from . import capture
+    if cap.stream.shape[1] != config.N_MICROPHONES:
+        raise ValueError("capture has %d channels per datagram, config.N_MICROPHONES is %d"
+                         % (cap.stream.shape[1], config.N_MICROPHONES))
+    return signals_from_blocks(capture.blocks(cap.stream, config.N_SAMPLES), cap.n_arrays, quirk, zero_mask, norm,
+                               rows, cols)

@@ -179,3 +179,51 @@ def run_ref_wrappers(signals):
                        stdout=subprocess.DEVNULL)
         z = np.load(os.path.join(tmp, "out.npz"))
         return z["pad"], z["lerp"]
+
+
+class RefReceiver:
+    """The reference's UDP receiver (PC/src/receiver.c, built as oracle/_ref/<cfg>/librecv.so) fed through a
+    socketpair: receive_and_write_to_buffer() turns N_SAMPLES datagrams (receiver.h:51-59) into the
+    [mic][sample] float buffer.  On the last odd row the reference reads one int PAST the payload
+    (receiver.c:140, `row + COLUMNS - x` with x = 0); the message buffer handed to it here is followed
+    by one extra int, `past_end`, so that read is defined and chosen by the test."""
+
+    def __init__(self, cfg):
+        self.g = general(cfg)
+        self.N, self.M = self.g["N_SAMPLES"], self.g["N_MICROPHONES"]
+        self.L = ctypes.CDLL(os.path.join(ROOT, cfg, "librecv.so"))
+
+    @staticmethod
+    def available(cfg):
+        return os.path.exists(os.path.join(ROOT, cfg, "librecv.so"))
+
+    def receive(self, stream, n_arrays, counter0=0, frequency=48828, version=2, past_end=0, ring=True):
+        """stream: int32 [N_SAMPLES][N_MICROPHONES] payloads -> float32 [N_MICROPHONES][N_SAMPLES]."""
+        import socket
+        import struct
+        import threading
+        stream = np.ascontiguousarray(stream, np.int32)
+        assert stream.shape == (self.N, self.M)
+        a, b = socket.socketpair(socket.AF_UNIX, socket.SOCK_DGRAM)
+        try:
+            def feed():
+                for i in range(self.N):
+                    a.send(struct.pack("<Hbbi", frequency, n_arrays, version, counter0 + i) + stream[i].tobytes())
+            th = threading.Thread(target=feed)
+            th.start()
+            msg = (ctypes.c_int32 * (2 + self.M + 1))()
+            msg[2 + self.M] = past_end
+            if ring:      # ring_buffer: int index; float data[4 * BUFFER_LENGTH]; int counter  (receiver.h:31-36)
+                rb = (ctypes.c_float * (1 + 4 * self.M * self.N + 1))()
+                rc = self.L.receive_and_write_to_buffer(ctypes.c_int(b.fileno()), rb, msg, ctypes.c_int(n_arrays))
+                assert rc == 0
+                out = np.frombuffer(rb, np.float32, self.M * self.N, 4).copy()
+            else:
+                buf = np.zeros(self.M * self.N, np.float32)
+                self.L.receive_to_buffer(ctypes.c_int(b.fileno()), _p(buf), msg, ctypes.c_int(n_arrays))
+                out = buf
+            th.join()
+        finally:
+            a.close()
+            b.close()
+        return out.reshape(self.M, self.N)

@@ -66,10 +66,11 @@ def _oracle(snaps, g, loading):
     return R, P, Pdas
 
 
-@pytest.mark.parametrize("tensor_cores", [0, 1, 2])
+@pytest.mark.parametrize("tensor_cores", [0, 1, 2, 3])
 def test_mvdr_against_float64_oracle_and_das_anchor(tensor_cores, monkeypatch):
-    """tensor_cores=2: warp-specialised tcgen05 steering contraction (3-pass split tf32), 1: its
-    single-buffered first version, 0: CUDA-core fp32."""
+    """tensor_cores=3 (default): warp-specialised tcgen05 steering contraction, kind::f16 with a two-term
+    fp16 split; 2: the same with kind::tf32 (3-pass split tf32); 1: its single-buffered first version;
+    0: CUDA-core fp32."""
     monkeypatch.setenv("BF_MVDR_TC", str(tensor_cores))
     g = gold("fd_das")
     bfa, nat, L = _setup()

@@ -42,3 +42,38 @@ def test_random_inputs_bitwise(case):
         assert bits_equal(w1, w2) and bits_equal(t1, t2)
         assert bits_equal(R.mimo_hybrid(sig, mics, d32), cpu.mimo_hybrid(sig, mics, d32, R.D, R.T))
         assert bits_equal(dm.compute_convolve_h(), dn.compute_convolve_h(cfg))
+
+
+@pytest.mark.skipif(not ref.RefReceiver.available("default"), reason="oracle/_ref/*/librecv.so not built")
+@pytest.mark.parametrize("case,n_arrays", [("default", 4), ("default", 2), ("c1", 1)])
+def test_ingest_restatement_vs_the_real_receiver(case, n_arrays):
+    """orc_ingest (the oracle the CUDA ingest kernel is tested against) == the reference's own
+    receive_and_write_to_buffer / receive_to_buffer (PC/src/receiver.c:94-151, 161-215), fed through a
+    socketpair, bit for bit -- including the off-by-one of the odd rows (quirk = 1).  The one read the
+    reference makes PAST the payload (last odd row of the last array when the arrays fill the datagram,
+    receiver.c:140 with x = 0) lands in an int the test owns: whatever sits there shows up in that one
+    channel; the restatement (and the device) read 0 there."""
+    import ctypes
+    R = ref.RefReceiver(case)
+    rng = np.random.default_rng(40 + n_arrays)
+    stream = rng.integers(-2 ** 23, 2 ** 23, (R.N, R.M), dtype=np.int32)
+    want = np.zeros((R.M, R.N), np.float32)
+    cpu.lib().orc_ingest(stream.ctypes.data_as(ctypes.c_void_p), want.ctypes.data_as(ctypes.c_void_p), R.N, R.M,
+                         n_arrays, 8, 8, ctypes.c_double(2.0 ** 24), 1)
+    n_ch = n_arrays * 64
+    for ring in (True, False):
+        got = R.receive(stream, n_arrays, counter0=77, past_end=0, ring=ring)
+        assert bits_equal(got[:n_ch], want[:n_ch]), (case, n_arrays, ring)
+    past = R.receive(stream, n_arrays, past_end=4242)
+    differ = np.flatnonzero((past[:n_ch].view(np.uint32) != want[:n_ch].view(np.uint32)).any(axis=1))
+    if n_ch == R.M:          # the arrays fill the datagram: channel n_ch - 8 reads stream[N_MICROPHONES]
+        assert list(differ) == [n_ch - 8] and np.all(past[n_ch - 8] == np.float32(4242 / 2.0 ** 24))
+    else:                    # otherwise the "next row" is still inside the payload
+        assert len(differ) == 0
+    # the fixed mapping (quirk = 0) differs from the reference exactly on the odd rows
+    fixed = np.zeros((R.M, R.N), np.float32)
+    cpu.lib().orc_ingest(stream.ctypes.data_as(ctypes.c_void_p), fixed.ctypes.data_as(ctypes.c_void_p), R.N, R.M,
+                         n_arrays, 8, 8, ctypes.c_double(2.0 ** 24), 0)
+    rows = (np.arange(n_ch) // 8) % 8
+    assert bits_equal(fixed[:n_ch][rows % 2 == 0], want[:n_ch][rows % 2 == 0])
+    assert not bits_equal(fixed[:n_ch][rows % 2 == 1], want[:n_ch][rows % 2 == 1])

@@ -29,22 +29,48 @@ def sources():
     return src
 
 
+OBJ_DIR = os.path.join(HERE, "build")
+
+
+def _headers():
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".inc", ".h"))]
+    deps.append(os.path.join(HERE, "..", "include", "bf_b200.h"))
+    return deps
+
+
 def stale():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
-    deps.append(os.path.join(HERE, "..", "include", "bf_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in sources() + _headers())
 
 
 def build(force=False, verbose=False):
+    """Compile every .cu to its own object (in parallel, only the stale ones), then link."""
     if not force and not stale():
         return OUT
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *sources(), "-o", OUT]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdr_t = max(os.path.getmtime(d) for d in _headers())
+    flags = [f for f in NVCC_FLAGS if f != "--shared"]
     if verbose:
-        cmd[1:1] = ["-Xptxas", "-v"]
+        flags += ["-Xptxas", "-v"]
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        if (not force and os.path.exists(obj)
+                and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t)):
+            return obj
+        cmd = [nvcc, *flags, "-c", src, "-o", obj]
+        print("+", " ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, sources()))
+    # -z defs: an undefined symbol is a link error here, not a dlopen failure on the GPU box
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-Xlinker", "-z,defs", *objs, "-o", OUT]
     print("+", " ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)
     return OUT

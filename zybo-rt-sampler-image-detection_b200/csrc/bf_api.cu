@@ -99,6 +99,29 @@ int ensure_pinned(size_t bytes)
 
 static std::mutex g_mu;   // part-1 calls share global tables/staging, like the reference
 
+// The device entry points (bf_*_dev) take a stream but share process-global scratch with every other call
+// (lerp first differences, group tables and FIR re-layouts built lazily on the first caller's stream, the
+// last-CTA ticket of the fused gather).  They are serialised here: the host side by g_mu, and the device
+// side by ordering a call behind the previous one whenever it arrives on a DIFFERENT stream (event
+// record on the old stream, wait on the new one).  Calls that stay on one stream pay nothing.
+static cudaStream_t g_last_stream = nullptr;
+static bool g_have_last_stream = false;
+static cudaEvent_t g_order_event = nullptr;
+static int order_behind_previous(cudaStream_t st)
+{
+    if (g_have_last_stream && g_last_stream != st) {
+        if (!g_order_event) BF_CUDA(cudaEventCreateWithFlags(&g_order_event, cudaEventDisableTiming));
+        if (cudaEventRecord(g_order_event, g_last_stream) == cudaSuccess) {
+            BF_CUDA(cudaStreamWaitEvent(st, g_order_event, 0));
+        } else {
+            cudaGetLastError();                  // the previous stream is gone: its work has completed
+        }
+    }
+    g_last_stream = st;
+    g_have_last_stream = true;
+    return BF_OK;
+}
+
 // ---- table installation --------------------------------------------------------
 static int install_pad(DevBuf &buf, size_t &count, int &wmax, GroupTable *gt, const int *src,
                        size_t n, bool src_on_device)
@@ -233,6 +256,7 @@ static int host_mimo(int algo, const float *signals, float *image, const int *ad
     State &S = state();
     int rc = ensure_device();
     if (rc) return rc;
+    if ((rc = order_behind_previous(0))) return rc;
     if ((rc = check_n(n, "mimo"))) return rc;
     const size_t sig_b = (size_t)S.cfg.n_microphones * S.cfg.n_samples * sizeof(float);
     const int D = S.cfg.max_res_x * S.cfg.max_res_y;
@@ -262,6 +286,7 @@ static int host_miso(int algo, const float *signals, float *out, const int *adap
     State &S = state();
     int rc = ensure_device();
     if (rc) return rc;
+    if ((rc = order_behind_previous(0))) return rc;
     if ((rc = check_n(n, "miso"))) return rc;
     const size_t sig_b = (size_t)S.cfg.n_microphones * S.cfg.n_samples * sizeof(float);
     const size_t out_b = (size_t)S.cfg.n_samples * sizeof(float);
@@ -372,10 +397,12 @@ int bf_mimo_dev_ex(int algo, const float *d_signals, float *d_images, int frames
                    const int *d_mic_ids, int n, int d_begin, int d_count, long frame_stride,
                    long dir_stride, int d_origin, void *stream)
 {
+    std::lock_guard<std::mutex> lk(g_mu);
     clear_error();
     State &S = state();
     int rc = ensure_device();
     if (rc) return rc;
+    if ((rc = order_behind_previous((cudaStream_t)stream))) return rc;
     if ((rc = check_n(n, "bf_mimo_dev"))) return rc;
     const int D = S.cfg.max_res_x * S.cfg.max_res_y;
     if (frames < 1 || d_begin < 0 || d_count < 1 || d_begin + d_count > D || !d_signals || !d_images || !d_mic_ids) {
@@ -401,10 +428,12 @@ int bf_mimo_dev_gather_sync(int algo, const float *d_signals, int frames, const 
                             long per_rank, void *const *flag_arrays, long long wait_seq, long long signal_seq,
                             int *d_timed_out, void *stream)
 {
+    std::lock_guard<std::mutex> lk(g_mu);
     clear_error();
     State &S = state();
     int rc = ensure_device();
     if (rc) return rc;
+    if ((rc = order_behind_previous((cudaStream_t)stream))) return rc;
     if ((rc = check_n(n, "bf_mimo_dev_gather"))) return rc;
     const int D = S.cfg.max_res_x * S.cfg.max_res_y;
     const int N = S.cfg.n_samples;
@@ -458,9 +487,11 @@ int bf_mimo_dev_gather_sync(int algo, const float *d_signals, int frames, const 
 int bf_miso_dev(int algo, const float *d_signals, float *d_out, int blocks, const int *d_mic_ids,
                 int n, int offset, int scale, void *stream)
 {
+    std::lock_guard<std::mutex> lk(g_mu);
     clear_error();
     int rc = ensure_device();
     if (rc) return rc;
+    if ((rc = order_behind_previous((cudaStream_t)stream))) return rc;
     if ((rc = check_n(n, "bf_miso_dev"))) return rc;
     if (blocks < 1 || offset < 0 || !d_signals || !d_out || !d_mic_ids) {
         set_error(BF_ERR_ARG, "bf_miso_dev: blocks %d offset %d", blocks, offset);
@@ -529,8 +560,10 @@ int bf_mimo_host_batch(int algo, const float *signals, float *images, int frames
         if ((rc = d_sig[i].ensure((size_t)chunk * sig_f * sizeof(float)))) return rc;
         if ((rc = d_img[i].ensure((size_t)chunk * D * sizeof(float)))) return rc;
     }
+    if ((rc = order_behind_previous(0))) return rc;
     if ((rc = upload_mics(adaptive_array, n))) return rc;
     BF_CUDA(cudaStreamSynchronize(0));
+    if ((rc = order_behind_previous(st_run))) return rc;
     const int nchunks = (int)c_size.size();
     auto drain = [&](int k) -> int {          // wait for chunk k's results, un-stage them
         const int sl = k & 1, f0 = c_start[k], fc = c_size[k];

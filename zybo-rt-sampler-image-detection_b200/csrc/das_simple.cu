@@ -188,7 +188,8 @@ int miso_simple(int algo, const float *d_sig, float *d_out, int blocks, const in
     if (N < 1 || N > 1024) { set_error(BF_ERR_CONFIG, "N_SAMPLES %d not in [1,1024]", N); return BF_ERR_CONFIG; }
     SimpleTab tb;
     const int talgo = by_mic_id ? -2 : algo;
-    size_t need = by_mic_id ? 1 : (size_t)offset + n;
+    // miso_pad2 indexes its table by microphone id (pad_and_sum.c:77-92): every id < N_MICROPHONES must be covered
+    size_t need = by_mic_id ? (size_t)S.cfg.n_microphones : (size_t)offset + n;
     if (algo == BF_ALGO_FIR_SEQ || algo == BF_ALGO_FIR_LANES)
         need = (size_t)offset / S.cfg.n_taps + n;        // FIR offsets are in floats (d*n*T)
     int rc = make_tab(talgo, tb, need, "miso");

@@ -34,6 +34,8 @@ struct FdState {
     DevBuf red;        // reductions
 };
 static FdState g_fd;
+static uint64_t g_fd_generation = 0;       // bumped by every bf_fd_setup: keys caches derived from the geometry
+uint64_t fd_geometry_generation() { return g_fd_generation; }
 
 // ---- geometry: u[d][m], float64, the reference's operation order -----------------------
 __global__ void fd_geometry_kernel(const double *__restrict__ xs, const double *__restrict__ ys,
@@ -172,6 +174,7 @@ int fd_setup(int n_mics, int n_samples, double fs, double c, int lo_bin, int hi_
     FdState &G = g_fd;
     G.n_mics = n_mics; G.n_active = n_active; G.N = n_samples; G.lo = lo_bin; G.hi = hi_bin;
     G.D = res_x * res_y; G.fs = fs; G.c = c;
+    g_fd_generation++;
     DevBuf tmp;
     const size_t nd = (size_t)res_x + res_y + 2 * (size_t)n_mics;
     if ((rc = tmp.ensure(nd * sizeof(double)))) return rc;

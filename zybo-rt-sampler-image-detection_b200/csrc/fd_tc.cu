@@ -28,10 +28,13 @@
 // First correct version: single-buffered (generate/copy, then MMA, then next chunk); the
 // pipelined, multicast version is the round-2 item.
 #include <math.h>
+#include <cuda_fp16.h>
 
 #include "bf_common.cuh"
 
 namespace bf {
+
+uint64_t fd_geometry_generation();          // fd_path.cu: bumped by every bf_fd_setup
 
 static constexpr int kTcDirs = 128;        // directions per CTA (MMA M)
 static constexpr int kTcKc = 32;           // K elements per chunk = 16 microphones (128-byte rows)
@@ -438,6 +441,264 @@ __global__ void __launch_bounds__(kV2Threads, 1) mvdr_tc_steer_kernel2(const uns
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+// ---- version 3: kind::f16 with a two-term fp16 split (round 2) -------------------------------------
+// Same roles, rings and TMEM layout as version 2, but the operands are fp16 (hi + lo, 11 + 11 significant
+// bits) and the MMAs are kind::f16, which run at twice the tf32 rate: three passes hi*hi + hi*lo + lo*hi cost
+// 1.5 bf16-equivalent passes instead of 3 tf32 ones (= 6).  A 128-byte operand row now holds 64 halves = 32
+// microphones, so a map needs 8 k-chunks instead of 16 and half the MMA instructions.
+// Range: fp16 has 5 exponent bits, so both operands are pre-scaled by exact powers of two -- the phasors by
+// 2^8 (|hi| <= 256, lo stays a normal number down to |x| = 2^-10) and every L^-1 row so that its largest
+// entry lies in [2^7, 2^8) (mvdr_tc_rowscale_kernel) -- and the epilogue multiplies column n of Y by
+// colscale[f][n] = 2^-(e_n + 8) before squaring (exact).  Absolute representation error per operand element:
+// <= 2^-25 of the row's largest entry (phasors: of 1).
+static constexpr int kV3Kc = 64;                                 // halves per 128-byte row = 32 microphones
+static constexpr int kV3Chunks = 2 * kTcMics / kV3Kc;            // 8
+static constexpr int kV3GenWarps = 16;
+static constexpr int kV3Threads = (6 + kV3GenWarps) * 32;        // 704
+__device__ __forceinline__ int v3_chunk(int i) { return (i & 1) ? kV3Chunks / 2 + (i >> 1) : (i >> 1); }
+
+// per (bin, microphone row i): exponent e with max_j(|Lr|,|Li|) * 2^e in [2^7, 2^8); colscale = 2^-(e+8)
+__global__ void mvdr_tc_rowscale_kernel(const float2 *__restrict__ linv, int *__restrict__ expo,
+                                        float *__restrict__ colscale)
+{
+    const int f = blockIdx.x, i = threadIdx.x;                   // 256 threads
+    const float2 *row = linv + ((size_t)f * kTcMics + i) * kTcMics;
+    float mx = 0.0f;
+    for (int j = 0; j <= i; j++) { const float2 l = row[j]; mx = fmaxf(mx, fmaxf(fabsf(l.x), fabsf(l.y))); }
+    int e = 0;
+    if (mx > 0.0f && isfinite(mx)) { int ex; frexpf(mx, &ex); e = 8 - ex; }      // mx = m * 2^ex, m in [0.5, 1)
+    expo[(size_t)f * kTcMics + i] = e;
+    const float sc = ldexpf(1.0f, -(e + 8));
+    colscale[((size_t)f * kTcMics + i) * 2] = sc;
+    colscale[((size_t)f * kTcMics + i) * 2 + 1] = sc;
+}
+
+// image3[f][chunk][plane hi/lo][row n = 2i+part][64 halves]   (k = 2*(j - 32*chunk) + {0: cos, 1: sin})
+__global__ void mvdr_tc_prep3_kernel(const float2 *__restrict__ linv, const int *__restrict__ expo,
+                                     unsigned char *__restrict__ image)
+{
+    const int f = blockIdx.y, chunk = blockIdx.x;
+    const float2 *L = linv + (size_t)f * kTcMics * kTcMics;
+    unsigned char *img = image + ((size_t)f * kV3Chunks + chunk) * 2 * kTcPlaneB;
+    for (int e = threadIdx.x; e < kTcRows * (kV3Kc / 2); e += blockDim.x) {       // one (row, microphone) pair per step
+        const int n = e / (kV3Kc / 2), jj = e - n * (kV3Kc / 2);
+        const int i = n >> 1, part = n & 1;
+        const int j = chunk * (kV3Kc / 2) + jj;
+        float vc = 0.0f, vs = 0.0f;                                            // multiplies cos_j / sin_j
+        if (j <= i) {
+            const float2 l = L[(size_t)i * kTcMics + j];
+            const int ex = expo[(size_t)f * kTcMics + i];
+            // part 0 (yr): cos -> Lr, sin -> -Li ; part 1 (yi): cos -> Li, sin -> Lr
+            vc = ldexpf(part == 0 ? l.x : l.y, ex);
+            vs = ldexpf(part == 0 ? -l.y : l.x, ex);
+        }
+        const __half2 hi = __floats2half2_rn(vc, vs);
+        const float2 hf = __half22float2(hi);
+        const __half2 lo = __floats2half2_rn(vc - hf.x, vs - hf.y);
+        const uint32_t off = swz128((uint32_t)n * 128u + (uint32_t)jj * 4u);
+        *(__half2 *)(img + off) = hi;
+        *(__half2 *)(img + kTcPlaneB + off) = lo;
+    }
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(kV3Threads, 1) mvdr_tc_steer_kernel3(const unsigned char *__restrict__ image,
+                                                                       const float2 *__restrict__ phi,
+                                                                       const float *__restrict__ colscale, int F, int lo,
+                                                                       int D, int tiles, float *__restrict__ qout)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *sA = smem;                                  // 2 x 32 KiB (hi + lo planes of 128 rows)
+    unsigned char *sB = smem + 2 * kV2BufA;                    // 2 x 64 KiB (hi + lo planes of 256 rows)
+    uint64_t *bars = (uint64_t *)(sB + 2 * kV2SlotB);
+    uint64_t *a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 6;
+    uint64_t *t0_done = bars + 8, *acc_done = bars + 9, *acc_free = bars + 10;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 11);
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int units = F * tiles;
+
+    if (t == 0) {
+        for (int i = 0; i < 2; i++) {
+            bfptx::mbar_init(&a_full[i], kV3GenWarps);
+            bfptx::mbar_init(&a_empty[i], 1);
+            bfptx::mbar_init(&b_full[i], 1);
+            bfptx::mbar_init(&b_empty[i], 1);
+        }
+        bfptx::mbar_init(t0_done, 1);
+        bfptx::mbar_init(acc_done, 1);
+        bfptx::mbar_init(acc_free, 4);
+        bfptx::fence_mbar_init();
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;"
+                     ::"r"(bfptx::smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 5) {
+        // ================= bulk-TMA producer: B slots ==================================================
+        if (lane == 0) {
+            uint32_t k = 0;
+            for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+                const int f = unit / tiles;
+                const unsigned char *img = image + (size_t)f * kV3Chunks * 2 * kTcPlaneB;
+                for (int ci = 0; ci < kV3Chunks; ci++) {
+                    const int chunk = v3_chunk(ci);
+                    for (int nt = (chunk < kV3Chunks / 2 ? 0 : 1); nt < 2; nt++, k++) {
+                        const uint32_t slot = k & 1, ph = (k >> 1) & 1;
+                        bfptx::mbar_wait(&b_empty[slot], ph ^ 1);
+                        unsigned char *dst = sB + slot * kV2SlotB;
+                        const unsigned char *src = img + (size_t)chunk * 2 * kTcPlaneB + (size_t)nt * 256 * 128;
+                        bfptx::mbar_arrive_expect_tx(&b_full[slot], (uint32_t)kV2SlotB);
+                        bfptx::bulk_g2s(dst, src, 256 * 128, &b_full[slot]);
+                        bfptx::bulk_g2s(dst + 256 * 128, src + kTcPlaneB, 256 * 128, &b_full[slot]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ================= MMA issuer =====================================================================
+        if (lane == 0) {
+            // D fp32, A / B fp16, both K-major, M = 128, N = 256
+            const uint32_t idesc = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+            uint32_t k = 0, g = 0, w = 0;
+            for (int unit = blockIdx.x; unit < units; unit += gridDim.x, w++) {
+                bfptx::mbar_wait(acc_free, (w & 1) ^ 1);
+                tc_fence_after();
+                bool first0 = true, first1 = true;               // first MMA into N-tile 0 / 1 overwrites
+                for (int ci = 0; ci < kV3Chunks; ci++, g++) {
+                    const int chunk = v3_chunk(ci);
+                    const uint32_t ab = g & 1, aph = (g >> 1) & 1;
+                    bfptx::mbar_wait(&a_full[ab], aph);
+                    const uint32_t a_hi = bfptx::smem_u32(sA + ab * kV2BufA), a_lo = a_hi + (uint32_t)kTcPlaneA;
+                    for (int nt = (chunk < kV3Chunks / 2 ? 0 : 1); nt < 2; nt++, k++) {
+                        const uint32_t slot = k & 1, ph = (k >> 1) & 1;
+                        bfptx::mbar_wait(&b_full[slot], ph);
+                        tc_fence_after();
+                        const uint32_t b_hi = bfptx::smem_u32(sB + slot * kV2SlotB), b_lo = b_hi + 256u * 128u;
+                        const uint32_t dcol = tmem + (uint32_t)nt * 256u;
+                        bool &first = nt == 0 ? first0 : first1;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++) {
+                            const uint32_t ko = (uint32_t)ks * 32u;          // 16 halves = 32 bytes per k-step
+                            umma_f16(dcol, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), idesc, first ? 0u : 1u);
+                            first = false;
+                            umma_f16(dcol, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_lo + ko), idesc, 1u);
+                            umma_f16(dcol, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_hi + ko), idesc, 1u);
+                        }
+                        umma_commit(&b_empty[slot]);
+                        if (nt == 0 && chunk == kV3Chunks / 2 - 1) umma_commit(t0_done);
+                    }
+                    umma_commit(&a_empty[ab]);
+                }
+                umma_commit(acc_done);
+            }
+        }
+    } else if (warp >= 6) {
+        // ================= phasor generators: A chunk buffers ==========================================
+        const int gt = t - 6 * 32;                               // 0..511
+        const int row = gt & 127, quarter = gt >> 7;             // direction row, which 8 of the chunk's 32 microphones
+        uint32_t g = 0;
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+            const int f = unit / tiles, tile = unit - f * tiles;
+            const int d = tile * kTcDirs + row;
+            const float4 *pr = (const float4 *)(phi + (size_t)(d < D ? d : D - 1) * kTcMics + quarter * 8);
+            const float bin = (float)(lo + f);
+            float4 p[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) p[i] = __ldg(pr + v3_chunk(0) * 16 + i);
+            for (int ci = 0; ci < kV3Chunks; ci++, g++) {
+                const uint32_t ab = g & 1, aph = (g >> 1) & 1;
+                float4 c[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) c[i] = p[i];
+                if (ci + 1 < kV3Chunks) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) p[i] = __ldg(pr + v3_chunk(ci + 1) * 16 + i);
+                }
+                uint32_t hi[8], lo8[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float ph_hi = (i & 1) ? c[i >> 1].z : c[i >> 1].x;
+                    const float ph_lo = (i & 1) ? c[i >> 1].w : c[i >> 1].y;
+                    float t1 = __fmul_rn(bin, ph_hi);              // exact: bin < 2^10, ph_hi multiple of 2^-12
+                    t1 = __fsub_rn(t1, rintf(t1));
+                    const float fr = __fmaf_rn(bin, ph_lo, t1);
+                    float sn, cs;
+                    sincospif(-2.0f * fr, &sn, &cs);
+                    cs *= 256.0f; sn *= 256.0f;
+                    const __half2 h = __floats2half2_rn(cs, sn);
+                    const float2 hf = __half22float2(h);
+                    const __half2 l = __floats2half2_rn(cs - hf.x, sn - hf.y);
+                    hi[i] = *(const uint32_t *)&h;
+                    lo8[i] = *(const uint32_t *)&l;
+                }
+                bfptx::mbar_wait(&a_empty[ab], aph ^ 1);
+                unsigned char *dst = sA + ab * kV2BufA;
+#pragma unroll
+                for (int cc = 0; cc < 2; cc++) {
+                    const uint32_t off = swz128((uint32_t)row * 128u + (uint32_t)(quarter * 2 + cc) * 16u);
+                    *(uint4 *)(dst + off) = make_uint4(hi[4 * cc], hi[4 * cc + 1], hi[4 * cc + 2], hi[4 * cc + 3]);
+                    *(uint4 *)(dst + kTcPlaneA + off) = make_uint4(lo8[4 * cc], lo8[4 * cc + 1], lo8[4 * cc + 2], lo8[4 * cc + 3]);
+                }
+                bfptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) bfptx::mbar_arrive(&a_full[ab]);
+            }
+        }
+    } else {
+        // ================= epilogue warps 0-3: q(d) = sum over 512 columns of (Y * colscale)^2 ========
+        uint32_t w = 0;
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x, w++) {
+            const int f = unit / tiles, tile = unit - f * tiles;
+            const int d = tile * kTcDirs + warp * 32 + lane;
+            const float4 *cs4 = (const float4 *)(colscale + (size_t)f * kTcRows);
+            float q = 0.0f;
+            bfptx::mbar_wait(t0_done, w & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < 512; c0 += 32) {
+                if (c0 == 256) { bfptx::mbar_wait(acc_done, w & 1); tc_fence_after(); }
+                float v[32];
+                tmem_ld32(lane_base + (uint32_t)c0, v);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float4 s4 = __ldg(cs4 + (c0 >> 2) + i);
+                    float x;
+                    x = v[4 * i] * s4.x;     q = fmaf(x, x, q);
+                    x = v[4 * i + 1] * s4.y; q = fmaf(x, x, q);
+                    x = v[4 * i + 2] * s4.z; q = fmaf(x, x, q);
+                    x = v[4 * i + 3] * s4.w; q = fmaf(x, x, q);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) bfptx::mbar_arrive(acc_free);
+            if (d < D) qout[(size_t)f * D + d] = q;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 // P[d] = sum_f 1/q[f][d]   (fixed order: deterministic)
 __global__ void mvdr_tc_reduce_kernel(const float *__restrict__ q, int F, int D, float *__restrict__ power)
 {
@@ -448,7 +709,23 @@ __global__ void mvdr_tc_reduce_kernel(const float *__restrict__ q, int F, int D,
     power[d] = p;
 }
 
-static DevBuf g_image, g_q;
+static DevBuf g_image, g_q, g_phi;
+
+// reduced phase table of the generators (mvdr_tc_phi_kernel), rebuilt when the geometry changes
+static int ensure_phi(const double *d_u, int D, int M, double scale, cudaStream_t st)
+{
+    static const double *phi_key = nullptr; static int phi_D = 0; static double phi_scale = 0.0;
+    static uint64_t phi_gen = ~0ull;
+    if (phi_key != d_u || phi_D != D || phi_scale != scale || phi_gen != fd_geometry_generation()) {
+        const size_t cnt = (size_t)D * M;
+        int rc = g_phi.ensure(cnt * sizeof(float2));
+        if (rc) return rc;
+        mvdr_tc_phi_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_u, cnt, scale, g_phi.as<float2>());
+        BF_CHECK_LAUNCH();
+        phi_key = d_u; phi_D = D; phi_scale = scale; phi_gen = fd_geometry_generation();
+    }
+    return BF_OK;
+}
 
 int mvdr_steer_tc(const float2 *d_linv, const double *d_u, int M, int F, int lo, double bin_hz, double inv_c,
                   int D, float *d_power, cudaStream_t st)
@@ -457,9 +734,32 @@ int mvdr_steer_tc(const float2 *d_linv, const double *d_u, int M, int F, int lo,
     int rc = g_image.ensure((size_t)F * kTcChunks * 2 * kTcPlaneB);
     if (rc) return rc;
     if ((rc = g_q.ensure((size_t)F * D * sizeof(float)))) return rc;
+    const int version = getenv("BF_MVDR_TC") ? atoi(getenv("BF_MVDR_TC")) : 3;
+    if (version >= 3) {
+        static DevBuf expo, colscale;
+        if ((rc = expo.ensure((size_t)F * kTcMics * sizeof(int)))) return rc;
+        if ((rc = colscale.ensure((size_t)F * kTcRows * sizeof(float)))) return rc;
+        mvdr_tc_rowscale_kernel<<<F, kTcMics, 0, st>>>(d_linv, expo.as<int>(), colscale.as<float>());
+        BF_CHECK_LAUNCH();
+        mvdr_tc_prep3_kernel<<<dim3(kV3Chunks, F), 256, 0, st>>>(d_linv, expo.as<int>(), g_image.as<unsigned char>());
+        BF_CHECK_LAUNCH();
+        const int tiles = (D + kTcDirs - 1) / kTcDirs;
+        const size_t smem = 2 * kV2BufA + 2 * kV2SlotB + 128;
+        BF_CUDA(cudaFuncSetAttribute(mvdr_tc_steer_kernel3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int units = tiles * F;
+        const int grid = units < state().sm_count ? units : state().sm_count;
+        if ((rc = ensure_phi(d_u, D, M, bin_hz * inv_c, st))) return rc;
+        if (lo + F > 1024) { set_error(BF_ERR_CONFIG, "tensor-core MVDR: bin index must stay below 1024"); return BF_ERR_CONFIG; }
+        mvdr_tc_steer_kernel3<<<grid, kV3Threads, smem, st>>>(g_image.as<unsigned char>(), g_phi.as<float2>(),
+                                                             colscale.as<float>(), F, lo, D, tiles, g_q.as<float>());
+        BF_CHECK_LAUNCH();
+        mvdr_tc_reduce_kernel<<<(D + 255) / 256, 256, 0, st>>>(g_q.as<float>(), F, D, d_power);
+        BF_CHECK_LAUNCH();
+        count_launch(5);
+        return BF_OK;
+    }
     mvdr_tc_prep_kernel<<<dim3(kTcChunks, F), 256, 0, st>>>(d_linv, g_image.as<unsigned char>());
     BF_CHECK_LAUNCH();
-    const int version = getenv("BF_MVDR_TC") ? atoi(getenv("BF_MVDR_TC")) : 2;
     if (version == 1) {
         const size_t smem = 2 * kTcPlaneA + 2 * kTcPlaneB + 64;
         BF_CUDA(cudaFuncSetAttribute(mvdr_tc_steer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -471,15 +771,8 @@ int mvdr_steer_tc(const float2 *d_linv, const double *d_u, int M, int F, int lo,
         BF_CUDA(cudaFuncSetAttribute(mvdr_tc_steer_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int units = tiles * F;
         const int grid = units < state().sm_count ? units : state().sm_count;
-        static DevBuf phi;
-        static const double *phi_key = nullptr; static int phi_D = 0; static double phi_scale = 0.0;
-        if (phi_key != d_u || phi_D != D || phi_scale != bin_hz * inv_c) {
-            const size_t cnt = (size_t)D * M;
-            if ((rc = phi.ensure(cnt * sizeof(float2)))) return rc;
-            mvdr_tc_phi_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_u, cnt, bin_hz * inv_c, phi.as<float2>());
-            BF_CHECK_LAUNCH();
-            phi_key = d_u; phi_D = D; phi_scale = bin_hz * inv_c;
-        }
+        if ((rc = ensure_phi(d_u, D, M, bin_hz * inv_c, st))) return rc;
+        DevBuf &phi = g_phi;
         if (lo + F > 1024) { set_error(BF_ERR_CONFIG, "tensor-core MVDR: bin index must stay below 1024"); return BF_ERR_CONFIG; }
         mvdr_tc_steer_kernel2<<<grid, kV2Threads, smem, st>>>(g_image.as<unsigned char>(), phi.as<float2>(), F, lo,
                                                              D, tiles, g_q.as<float>());

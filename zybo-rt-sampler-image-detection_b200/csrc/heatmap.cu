@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(512) entropy_kernel(const unsigned char *__res
 // ---------------------------------------------------------------------------------------------
 struct HeatState {
     std::mutex mu;
-    DevBuf lut; bool lut_set = false;
+    DevBuf lut; bool lut_set = false; bool lut_is_default = false;
     unsigned char lut_host[768];
     DevBuf xofs, xco, yco, ystart;
     int key[4] = {-1, -1, -1, -1};
@@ -403,18 +403,20 @@ static int ensure_lut(const unsigned char *lut, cudaStream_t st)
 {
     HeatState &H = hs();
     unsigned char tmp[768];
-    if (!lut) {
-        if (H.lut_set) return BF_OK;
+    if (!lut) {                                  // NULL = the default jet map, whatever was installed before
+        if (H.lut_set && H.lut_is_default) return BF_OK;
         jet_lut(tmp);
         lut = tmp;
     }
-    if (H.lut_set && memcmp(lut, H.lut_host, 768) == 0) return BF_OK;
+    const bool is_default = (lut == tmp);
+    if (H.lut_set && memcmp(lut, H.lut_host, 768) == 0) { H.lut_is_default = is_default; return BF_OK; }
     int rc = H.lut.ensure(768);
     if (rc) return rc;
     memcpy(H.lut_host, lut, 768);
     BF_CUDA(cudaMemcpyAsync(H.lut.p, H.lut_host, 768, cudaMemcpyHostToDevice, st));
     BF_CUDA(cudaStreamSynchronize(st));
     H.lut_set = true;
+    H.lut_is_default = is_default;
     return BF_OK;
 }
 

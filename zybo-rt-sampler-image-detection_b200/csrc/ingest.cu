@@ -106,7 +106,7 @@ __global__ void window_kernel(const float *__restrict__ rec, long samples, const
     const long s0 = starts[f];
     const float *src = rec + (size_t)m * samples + s0;
     float *dst = out + ((size_t)f * n_mics + m) * N;
-    for (int t = threadIdx.x; t < N; t += blockDim.x) dst[t] = (s0 + t < samples) ? src[t] : 0.0f;
+    for (int t = threadIdx.x; t < N; t += blockDim.x) dst[t] = (s0 + t >= 0 && s0 + t < samples) ? src[t] : 0.0f;   // outside the recording: silence
 }
 }  // namespace bf
 

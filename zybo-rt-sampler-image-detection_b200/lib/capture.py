@@ -118,7 +118,10 @@ def read_capture(path, n_microphones=256):
                          % (path, size, n_microphones, other))
     counter = np.array(counters, np.int64)
     gaps = np.diff(counter) & 0xFFFFFFFF
-    dropped = int(np.sum(gaps[gaps > 1] - 1))
+    # forward jumps of 2..2^31 are losses; a gap of 0 (duplicate) or >= 2^31 (a datagram that arrived
+    # late, i.e. a backward step modulo 2^32) is reordering, not loss
+    lost = gaps[(gaps > 1) & (gaps < (1 << 31))]
+    dropped = int(np.sum(lost - 1))
     return Capture(np.ascontiguousarray(np.stack(rows)), counter, np.array(stamps), hdr[0], hdr[1], hdr[2], dropped)
 
 

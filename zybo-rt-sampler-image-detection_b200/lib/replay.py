@@ -18,9 +18,10 @@ def frame_starts(n_frames, fs=48828, fps=30, first=0):
 
 
 def n_frames_in(total_samples, fs=48828, fps=30):
-    """Number of complete N_SAMPLES windows available."""
+    """Number of complete N_SAMPLES windows available: frames k with floor(k*fs/fps) <= last start,
+    i.e. k*fs < (last+1)*fps (same integer arithmetic as frame_starts)."""
     last = total_samples - config.N_SAMPLES
-    return 0 if last < 0 else int((last * int(fps)) // int(fs)) + 1
+    return 0 if last < 0 else int(((last + 1) * int(fps) + int(fs) - 1) // int(fs))
 
 
 def replay_dev(algo, d_recording, d_mic_ids, n, fps=30, fs=48828, chunk=64, rank=0, world=1, out=None):

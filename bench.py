@@ -52,12 +52,32 @@ WORKLOADS = {
 }
 
 
+def _source_sha(files):
+    """Short hash of the kernel sources a profile entry belongs to."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in files:
+        with open(os.path.join(PKG, "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:12]
+
+
 def _traffic(key):
-    """Per-launch DRAM traffic (or another ncu-derived figure) recorded in profiles/traffic.json."""
+    """Per-launch DRAM traffic (or another ncu-derived figure) recorded in profiles/traffic.json.
+    Every entry names the kernel sources it was captured from and their hash; an entry whose sources have
+    changed since the capture is STALE and is not reported (None) rather than printed as if it were current."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(path):
-        return json.load(open(path)).get(key)
-    return None
+    if not os.path.exists(path):
+        return None
+    e = json.load(open(path)).get(key)
+    if not isinstance(e, dict):
+        return None
+    try:
+        if _source_sha(e["sources"]) != e["source_sha"]:
+            return None
+    except (KeyError, OSError):
+        return None
+    return e["value"]
 
 
 def peaks():
@@ -224,7 +244,8 @@ def mvdr_c4(nat, L, torch, stream, bins=512, dirs=32768, K=64):
     """BASELINE config C4: frequency-domain MVDR, 256 mics, 1024-point FFT, bins 1..512, K = 64
     snapshots, 256 x 128 directions.  Useful flops of the steering contraction: 8*D*M^2*F
     (SURVEY.md 8d).  Tensor roofline = useful flops / steering-kernel time against the measured
-    dense bf16 peak; the kernel issues 2.25x that in tf32 (3-pass split, -25 % triangular skip)."""
+    dense bf16 peak; the kernel issues 2.25x that as kind::f16 MMAs (3-pass two-term fp16 split, -25 %
+    triangular skip)."""
     import realtime_scripts.calc_r_prime as rp
     import realtime_scripts.config as cfg
     M, N, F = 256, 1024, bins
@@ -266,11 +287,11 @@ def mvdr_c4(nat, L, torch, stream, bins=512, dirs=32768, K=64):
             "stage_ms": dict(zip(["fft_f64", "covariance_f64", "cholesky_f64", "tri_inverse_f64", "steering_tcgen05"],
                                  [float(x) for x in stage])),
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                         "kernel": "mvdr_tc_steer_kernel (tcgen05 kind::tf32, 3-pass split)",
+                         "kernel": "mvdr_tc_steer_kernel3 (tcgen05 kind::f16, 3-pass two-term fp16 split)",
                          "kernel_ms": float(stage[4]), "useful_flops_per_launch": useful,
                          "issued_over_useful": 2.25, "traffic": None,
                          "tensor_pipe_active_pct_ncu": _traffic("mvdr_tc_steer_tensor_pipe_active_pct"),
-                         "peak_source": "measured dense bf16 burst (MEASURED_PEAKS.json); tf32 peaks at half of it"}}
+                         "peak_source": "measured dense bf16 burst (MEASURED_PEAKS.json)"}}
 
 
 def replay_c5_sharded_local(torch, nat, algo, d_mics, n, D, M, N, rank):
@@ -442,6 +463,94 @@ def fir_default(nat, L, config, torch, stream, clocks):
         res[name] = {"maps_per_s": F / (ms * 1e-3), "gfma_per_s": fma / 1e9, "kernel_ms": ms,
                      "fp32_frac_of_148x128_lanes": fma / fp32, "kernel": "das_fir_kernel"}
     return res
+
+
+def e2e_sharded(torch, dist, nat, L, algo, d_pool, d_mics, n, D, F, M, N, rank, world, steps):
+    """End to end through the DIRECTION-SHARDED path (the partition `value` measures at N > 1): every step the
+    F frames of the batch are copied host -> device on every rank (each GPU has its own PCIe link; the host
+    batch is the same pinned buffer content on all ranks), each rank computes its direction slice with the
+    fused kernel + NVLink peer stores, and rank 0 copies the assembled [F][D] maps device -> host.  All copies
+    are inside the timed region; H2D of step i+1 and D2H of step i-1 overlap the kernel of step i (three
+    streams).  Returns maps/s (max over ranks) or None when peer memory is unavailable."""
+    from lib.sharded import PeerGather, assemble_peer_layout
+    try:
+        peer = PeerGather(D, F, rank, world, dist, depth=4, consume_lag=1)
+    except RuntimeError:
+        return None
+    frame_bytes = M * N * 4
+    n_host = min(d_pool.shape[0], 3)
+    h_in = torch.empty((n_host, F, M, N), dtype=torch.float32).pin_memory()
+    h_in.copy_(d_pool[:n_host].cpu())
+    h_out = torch.empty((2, F, D), dtype=torch.float32).pin_memory() if rank == 0 else None
+    d_in = torch.empty((2, F, M, N), device="cuda")
+    d_asm = torch.empty((2, F, D), device="cuda") if rank == 0 else None
+    s_in, s_run, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_run = [torch.cuda.Event() for _ in range(2)]
+    ev_asm = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+
+    def run(count, base):
+        for j in range(count):
+            i = base + j
+            sl = i & 1
+            with torch.cuda.stream(s_in):
+                if j >= 2:
+                    s_in.wait_event(ev_run[sl])                  # the kernel that read this slot has finished
+                d_in[sl].copy_(h_in[i % n_host], non_blocking=True)
+                ev_in[sl].record(s_in)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(ev_in[sl])
+                peer.step(i, algo, d_in[sl], d_mics, n, s_run.cuda_stream)
+                ev_run[sl].record(s_run)
+                if rank == 0 and j >= 1:                         # consume step i-1 behind the launch of step i
+                    pv = (i - 1) & 1
+                    if j >= 3:
+                        s_run.wait_event(ev_out[pv])             # its previous D2H has left the assembly buffer
+                    view = peer.ready(i - 1, s_run.cuda_stream)
+                    d_asm[pv].copy_(assemble_peer_layout(view, D))
+                    ev_asm[pv].record(s_run)
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(ev_asm[pv])
+                        h_out[pv].copy_(d_asm[pv], non_blocking=True)
+                        ev_out[pv].record(s_out)
+        if rank == 0:                                            # drain the last step
+            i = base + count - 1
+            pv = i & 1
+            with torch.cuda.stream(s_run):
+                view = peer.ready(i, s_run.cuda_stream)
+                d_asm[pv].copy_(assemble_peer_layout(view, D))
+                ev_asm[pv].record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_asm[pv])
+                h_out[pv].copy_(d_asm[pv], non_blocking=True)
+        for st in (s_in, s_run, s_out):
+            st.synchronize()
+
+    run(3, 0)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run(steps, 3)
+    dt = time.perf_counter() - t0
+    peer.check()
+    ok = None
+    if rank == 0:                                                # the maps that reached the host == one-GPU maps
+        last = 3 + steps - 1
+        full = torch.zeros((F, D), device="cuda")
+        nat.check(L.bf_mimo_dev_ex(algo, d_in[last & 1].data_ptr(), full.data_ptr(), F, d_mics.data_ptr(), n,
+                                   0, D, D, 1, 0, None))
+        torch.cuda.synchronize()
+        ok = bool(torch.equal(full.cpu(), h_out[last & 1]))
+    t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    peer.close()
+    return {"value": steps * F / float(t[0]), "unit": "maps/s", "steps": steps,
+            "h2d_bytes_per_step_per_rank": F * frame_bytes, "d2h_bytes_per_step_rank0": F * D * 4,
+            "host_maps_bit_exact_vs_one_gpu": ok,
+            "api": "host batch in (pinned, every rank) -> bf_mimo_dev_gather_sync (this rank's direction slice, peer "
+                   "stores) -> assembled maps out to the host on rank 0; copies inside the timed region"}
 
 
 # ----------------------------------------------------------------------------------------
@@ -700,6 +809,13 @@ def main():
                                       "call, pageable host memory, synchronous" % args.algo,
                                "ms_per_map": 1e3 * float(te[1]) / single_maps}}
         del h_pool, h_maps
+        if world > 1 and peer is not None:
+            try:
+                sh = e2e_sharded(torch, dist, nat, L, algo, d_pool, d_mics, n, D, F, M, N, rank, world, e2e_steps)
+            except Exception as ex:  # noqa: BLE001  (every rank reaches the collectives inside or none does)
+                sh = {"error": str(ex)}
+            e2e["partition"] = "replicas: each rank replays its own frames (recordings shard with no collective)"
+            e2e["sharded"] = sh
 
         # ---- extra: BASELINE config C5 (bounded sample), then C2 and C4 -----------------------
         if world > 1 and args.workload == "c3":
@@ -758,8 +874,11 @@ def main():
                            world, (", all-gather fused into the kernel: epilogue stores go to every rank's buffer over NVLink peer memory"
                             if peer else ", one in-place NCCL all-gather per step on a second stream") if world > 1 else ""),
                        "exact_sum": args.exact_sum},
-            "sum_step_ms": dev_ms, "wall_s": t_wall, "gather_check": gather_check, "gather_note": gather_note, "gpu_launches": launches, "clocks": clocks,
+            "sum_step_ms": dev_ms, "wall_s": t_wall, "gather_note": gather_note, "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "miso": miso, "mvdr": mvdr, "replay": replay, "heatmap": heat, "fir": fir,
+            # last on purpose: the tail of the line is what a truncated log keeps
+            "e2e_sharded_maps_per_s": (e2e or {}).get("sharded", {}).get("value") if isinstance((e2e or {}).get("sharded"), dict) else None,
+            "gather_check": gather_check,
         }
         print(json.dumps(line))
     if world > 1:

@@ -447,30 +447,41 @@ __global__ void __launch_bounds__(kV2Threads, 1) mvdr_tc_steer_kernel2(const uns
 // 1.5 bf16-equivalent passes instead of 3 tf32 ones (= 6).  A 128-byte operand row now holds 64 halves = 32
 // microphones, so a map needs 8 k-chunks instead of 16 and half the MMA instructions.
 // Range: fp16 has 5 exponent bits, so both operands are pre-scaled by exact powers of two -- the phasors by
-// 2^8 (|hi| <= 256, lo stays a normal number down to |x| = 2^-10) and every L^-1 row so that its largest
-// entry lies in [2^7, 2^8) (mvdr_tc_rowscale_kernel) -- and the epilogue multiplies column n of Y by
-// colscale[f][n] = 2^-(e_n + 8) before squaring (exact).  Absolute representation error per operand element:
-// <= 2^-25 of the row's largest entry (phasors: of 1).
+// 2^8 (|hi| <= 256, lo stays a normal number down to |x| = 2^-10) and the L^-1 of every bin so that its largest
+// entry lies in [2^7, 2^8) (mvdr_tc_rowscale_kernel) -- and the epilogue multiplies q by binscale[f]^2 =
+// 2^-2(e_f + 8) (exact).  Absolute representation error per operand element: <= 2^-25 of the bin's largest
+// entry (phasors: of 1).
 static constexpr int kV3Kc = 64;                                 // halves per 128-byte row = 32 microphones
 static constexpr int kV3Chunks = 2 * kTcMics / kV3Kc;            // 8
 static constexpr int kV3GenWarps = 16;
 static constexpr int kV3Threads = (6 + kV3GenWarps) * 32;        // 704
 __device__ __forceinline__ int v3_chunk(int i) { return (i & 1) ? kV3Chunks / 2 + (i >> 1) : (i >> 1); }
 
-// per (bin, microphone row i): exponent e with max_j(|Lr|,|Li|) * 2^e in [2^7, 2^8); colscale = 2^-(e+8)
+// per bin: exponent e with max_ij(|Lr|,|Li|) * 2^e in [2^7, 2^8); binscale = 2^-(e+8) undoes it and the 2^8 of the
+// phasors.  One scale per bin (not per row) keeps the epilogue free of per-column loads; rows whose entries
+// are up to 2^6 below the bin's largest still keep a normal-range lo part, and the absolute error of
+// any element stays <= 2^-25 of the bin's largest entry (cond(R) <= M / loading bounds the spread of the rows).
 __global__ void mvdr_tc_rowscale_kernel(const float2 *__restrict__ linv, int *__restrict__ expo,
-                                        float *__restrict__ colscale)
+                                        float *__restrict__ binscale)
 {
-    const int f = blockIdx.x, i = threadIdx.x;                   // 256 threads
+    __shared__ float red[kTcMics];
+    const int f = blockIdx.x, i = threadIdx.x;                   // 256 threads, one per row
     const float2 *row = linv + ((size_t)f * kTcMics + i) * kTcMics;
     float mx = 0.0f;
     for (int j = 0; j <= i; j++) { const float2 l = row[j]; mx = fmaxf(mx, fmaxf(fabsf(l.x), fabsf(l.y))); }
-    int e = 0;
-    if (mx > 0.0f && isfinite(mx)) { int ex; frexpf(mx, &ex); e = 8 - ex; }      // mx = m * 2^ex, m in [0.5, 1)
-    expo[(size_t)f * kTcMics + i] = e;
-    const float sc = ldexpf(1.0f, -(e + 8));
-    colscale[((size_t)f * kTcMics + i) * 2] = sc;
-    colscale[((size_t)f * kTcMics + i) * 2 + 1] = sc;
+    red[i] = mx;
+    __syncthreads();
+    for (int s = kTcMics / 2; s > 0; s >>= 1) {
+        if (i < s) red[i] = fmaxf(red[i], red[i + s]);
+        __syncthreads();
+    }
+    if (i == 0) {
+        mx = red[0];
+        int e = 0;
+        if (mx > 0.0f && isfinite(mx)) { int ex; frexpf(mx, &ex); e = 8 - ex; }      // mx = m * 2^ex, m in [0.5, 1)
+        expo[f] = e;
+        binscale[f] = ldexpf(1.0f, -(e + 8));
+    }
 }
 
 // image3[f][chunk][plane hi/lo][row n = 2i+part][64 halves]   (k = 2*(j - 32*chunk) + {0: cos, 1: sin})
@@ -487,7 +498,7 @@ __global__ void mvdr_tc_prep3_kernel(const float2 *__restrict__ linv, const int 
         float vc = 0.0f, vs = 0.0f;                                            // multiplies cos_j / sin_j
         if (j <= i) {
             const float2 l = L[(size_t)i * kTcMics + j];
-            const int ex = expo[(size_t)f * kTcMics + i];
+            const int ex = expo[f];
             // part 0 (yr): cos -> Lr, sin -> -Li ; part 1 (yi): cos -> Li, sin -> Lr
             vc = ldexpf(part == 0 ? l.x : l.y, ex);
             vs = ldexpf(part == 0 ? -l.y : l.x, ex);
@@ -512,11 +523,86 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         : "memory");
 }
 
-__global__ void __launch_bounds__(kV3Threads, 1) mvdr_tc_steer_kernel3(const unsigned char *__restrict__ image,
-                                                                       const float2 *__restrict__ phi,
-                                                                       const float *__restrict__ colscale, int F, int lo,
-                                                                       int D, int tiles, float *__restrict__ qout)
+// Phase table of version 3: tau(d, m) = u[d][m] * bin_hz / c in TURNS per bin index, reduced modulo 1 and stored
+// as 32-bit fixed point.  The phase of bin b is then the low 32 bits of b * fix -- an exact integer multiply that
+// wraps modulo one turn by itself -- with 2^-33 turns of quantisation per bin index (6e-8 turns at bin 512).
+// Layout [tile][chunk][i][quarter][row]: the 32 lanes of a generator warp (32 consecutive rows = directions,
+// one quarter) read 128 consecutive bytes per load.
+__global__ void mvdr_tc_phifix_kernel(const double *__restrict__ u, int D, double bin_hz_over_c, int tiles,
+                                      uint32_t *__restrict__ fix)
 {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)tiles * kTcMics * kTcDirs;
+    if (idx >= total) return;
+    const int row = (int)(idx % kTcDirs);
+    const int quarter = (int)((idx / kTcDirs) % 4);
+    const int i = (int)((idx / (kTcDirs * 4)) % 8);
+    const int chunk = (int)((idx / (kTcDirs * 32)) % 8);
+    const int tile = (int)(idx / ((size_t)kTcDirs * kTcMics));
+    int d = tile * kTcDirs + row;
+    if (d >= D) d = D - 1;
+    const int m = chunk * 32 + quarter * 8 + i;
+    const double tau = u[(size_t)d * kTcMics + m] * bin_hz_over_c;
+    const double fr = tau - floor(tau);                              // [0, 1)
+    fix[idx] = (uint32_t)(unsigned long long)llrint(fr * 4294967296.0);   // 2^32 wraps to 0
+}
+
+// (cos, -sin) of 2 pi x / 2^32 for a 32-bit fixed-point phase x (turns): the phasor exp(-j 2 pi x / 2^32).
+// Quadrant by integer arithmetic, then fp32 polynomials on [-pi/4, pi/4] (truncation error < 2e-9).
+__device__ __forceinline__ void phasor_fix(uint32_t x, float &cs, float &sn)
+{
+    const uint32_t q = (x + 0x20000000u) >> 30;                      // nearest quarter turn, 0..3 (4 wraps to 0)
+    const int32_t r = (int32_t)(x - (q << 30));                      // [-2^29, 2^29)
+    const float z = (float)r * 1.4629180792671596e-09f;              // 2 pi / 2^32
+    const float z2 = z * z;
+    float s = fmaf(z2, 2.7557319e-06f, -1.9841270e-04f);             // z - z^3/3! + z^5/5! - z^7/7! + z^9/9!
+    s = fmaf(s, z2, 8.3333333e-03f);
+    s = fmaf(s, z2, -1.6666667e-01f);
+    s = fmaf(s * z2, z, z);
+    float c = fmaf(z2, -2.7557319e-07f, 2.4801587e-05f);             // 1 - z^2/2! + z^4/4! - z^6/6! + z^8/8! - z^10/10!
+    c = fmaf(c, z2, -1.3888889e-03f);
+    c = fmaf(c, z2, 4.1666667e-02f);
+    c = fmaf(c, z2, -0.5f);
+    c = fmaf(c, z2, 1.0f);
+    // angle = q * pi/2 + z:  cos, sin = (c, s), (-s, c), (-c, -s), (s, -c)
+    const float a = (q & 1u) ? s : c, b = (q & 1u) ? c : s;
+    const float co = ((q + 1u) & 2u) ? -a : a;
+    const float si = (q & 2u) ? -b : b;
+    cs = co;
+    sn = -si;
+}
+
+// Issued by ALL lanes of the MMA warp: elect.sync picks one lane and only that lane's instruction is
+// predicated on.  Keeping the warp converged (no `if (lane == 0)` region) lets the compiler hold the
+// descriptors in uniform registers; inside a one-lane branch every UTCHMMA was preceded by R2UR moves and
+// cost the issuing thread ~170 cycles (ncu, round 2), more than the MMA itself takes.
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t *bar)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bfptx::smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kV3Threads, 1) mvdr_tc_steer_kernel3(const unsigned char *__restrict__ image,
+                                                                       const uint32_t *__restrict__ phifix,
+                                                                       const float *__restrict__ colscale, int F, int lo,
+                                                                       int D, int tiles, float *__restrict__ qout, int dbg)
+{
+    // dbg (BF_MVDR_DBG, timing experiments only -- results are wrong): bit 0 generators skip the sincos,
+    // bit 1 the producer skips the B copies
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sA = smem;                                  // 2 x 32 KiB (hi + lo planes of 128 rows)
     unsigned char *sB = smem + 2 * kV2BufA;                    // 2 x 64 KiB (hi + lo planes of 256 rows)
@@ -525,7 +611,10 @@ __global__ void __launch_bounds__(kV3Threads, 1) mvdr_tc_steer_kernel3(const uns
     uint64_t *t0_done = bars + 8, *acc_done = bars + 9, *acc_free = bars + 10;
     uint32_t *tmem_slot = (uint32_t *)(bars + 11);
 
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int t = threadIdx.x, lane = t & 31;
+    // warp index as a warp-uniform value: the role dispatch below is then a uniform branch and the MMA warp's
+    // addresses / descriptors can live in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
     const int units = F * tiles;
 
     if (t == 0) {
@@ -564,6 +653,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) mvdr_tc_steer_kernel3(const uns
                         bfptx::mbar_wait(&b_empty[slot], ph ^ 1);
                         unsigned char *dst = sB + slot * kV2SlotB;
                         const unsigned char *src = img + (size_t)chunk * 2 * kTcPlaneB + (size_t)nt * 256 * 128;
+                        if (dbg & 2) { bfptx::mbar_arrive(&b_full[slot]); continue; }
                         bfptx::mbar_arrive_expect_tx(&b_full[slot], (uint32_t)kV2SlotB);
                         bfptx::bulk_g2s(dst, src, 256 * 128, &b_full[slot]);
                         bfptx::bulk_g2s(dst + 256 * 128, src + kTcPlaneB, 256 * 128, &b_full[slot]);
@@ -573,40 +663,44 @@ __global__ void __launch_bounds__(kV3Threads, 1) mvdr_tc_steer_kernel3(const uns
         }
     } else if (warp == 4) {
         // ================= MMA issuer =====================================================================
-        if (lane == 0) {
+        {
             // D fp32, A / B fp16, both K-major, M = 128, N = 256
             const uint32_t idesc = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t a_base = bfptx::smem_u32(sA), b_base = bfptx::smem_u32(sB);
             uint32_t k = 0, g = 0, w = 0;
             for (int unit = blockIdx.x; unit < units; unit += gridDim.x, w++) {
                 bfptx::mbar_wait(acc_free, (w & 1) ^ 1);
                 tc_fence_after();
-                bool first0 = true, first1 = true;               // first MMA into N-tile 0 / 1 overwrites
+                uint32_t acc0 = 0u, acc1 = 0u;                   // first MMA into N-tile 0 / 1 overwrites
                 for (int ci = 0; ci < kV3Chunks; ci++, g++) {
                     const int chunk = v3_chunk(ci);
                     const uint32_t ab = g & 1, aph = (g >> 1) & 1;
                     bfptx::mbar_wait(&a_full[ab], aph);
-                    const uint32_t a_hi = bfptx::smem_u32(sA + ab * kV2BufA), a_lo = a_hi + (uint32_t)kTcPlaneA;
+                    tc_fence_after();
+                    const uint64_t da_hi = umma_desc_sw128(a_base + ab * (uint32_t)kV2BufA);
+                    const uint64_t da_lo = umma_desc_sw128(a_base + ab * (uint32_t)kV2BufA + (uint32_t)kTcPlaneA);
                     for (int nt = (chunk < kV3Chunks / 2 ? 0 : 1); nt < 2; nt++, k++) {
                         const uint32_t slot = k & 1, ph = (k >> 1) & 1;
                         bfptx::mbar_wait(&b_full[slot], ph);
                         tc_fence_after();
-                        const uint32_t b_hi = bfptx::smem_u32(sB + slot * kV2SlotB), b_lo = b_hi + 256u * 128u;
+                        const uint64_t db_hi = umma_desc_sw128(b_base + slot * (uint32_t)kV2SlotB);
+                        const uint64_t db_lo = umma_desc_sw128(b_base + slot * (uint32_t)kV2SlotB + 256u * 128u);
                         const uint32_t dcol = tmem + (uint32_t)nt * 256u;
-                        bool &first = nt == 0 ? first0 : first1;
+                        const uint32_t acc = nt == 0 ? acc0 : acc1;
 #pragma unroll
                         for (int ks = 0; ks < 4; ks++) {
-                            const uint32_t ko = (uint32_t)ks * 32u;          // 16 halves = 32 bytes per k-step
-                            umma_f16(dcol, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), idesc, first ? 0u : 1u);
-                            first = false;
-                            umma_f16(dcol, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_lo + ko), idesc, 1u);
-                            umma_f16(dcol, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_hi + ko), idesc, 1u);
+                            const uint64_t ko = (uint64_t)(ks * 2);          // 16 halves = 32 bytes = 2 descriptor units
+                            umma_f16_elect(dcol, da_hi + ko, db_hi + ko, idesc, ks == 0 ? acc : 1u);
+                            umma_f16_elect(dcol, da_hi + ko, db_lo + ko, idesc, 1u);
+                            umma_f16_elect(dcol, da_lo + ko, db_hi + ko, idesc, 1u);
                         }
-                        umma_commit(&b_empty[slot]);
-                        if (nt == 0 && chunk == kV3Chunks / 2 - 1) umma_commit(t0_done);
+                        if (nt == 0) acc0 = 1u; else acc1 = 1u;
+                        umma_commit_elect(&b_empty[slot]);
+                        if (nt == 0 && chunk == kV3Chunks / 2 - 1) umma_commit_elect(t0_done);
                     }
-                    umma_commit(&a_empty[ab]);
+                    umma_commit_elect(&a_empty[ab]);
                 }
-                umma_commit(acc_done);
+                umma_commit_elect(acc_done);
             }
         }
     } else if (warp >= 6) {
@@ -616,31 +710,28 @@ __global__ void __launch_bounds__(kV3Threads, 1) mvdr_tc_steer_kernel3(const uns
         uint32_t g = 0;
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
             const int f = unit / tiles, tile = unit - f * tiles;
-            const int d = tile * kTcDirs + row;
-            const float4 *pr = (const float4 *)(phi + (size_t)(d < D ? d : D - 1) * kTcMics + quarter * 8);
-            const float bin = (float)(lo + f);
-            float4 p[4];
+            // fixed-point phases of this thread's 8 microphones per chunk: [chunk][i][quarter][row]
+            const uint32_t *pf = phifix + (size_t)tile * (kTcMics * kTcDirs) + quarter * kTcDirs + row;
+            const uint32_t bin = (uint32_t)(lo + f);
+            uint32_t p[8], pn[8];                                 // next chunk, the one after (loads two chunks ahead)
 #pragma unroll
-            for (int i = 0; i < 4; i++) p[i] = __ldg(pr + v3_chunk(0) * 16 + i);
+            for (int i = 0; i < 8; i++) p[i] = __ldg(pf + (v3_chunk(0) * 8 + i) * (4 * kTcDirs));
+#pragma unroll
+            for (int i = 0; i < 8; i++) pn[i] = __ldg(pf + (v3_chunk(1) * 8 + i) * (4 * kTcDirs));
             for (int ci = 0; ci < kV3Chunks; ci++, g++) {
                 const uint32_t ab = g & 1, aph = (g >> 1) & 1;
-                float4 c[4];
+                uint32_t c[8];
 #pragma unroll
-                for (int i = 0; i < 4; i++) c[i] = p[i];
-                if (ci + 1 < kV3Chunks) {
+                for (int i = 0; i < 8; i++) { c[i] = p[i]; p[i] = pn[i]; }
+                if (ci + 2 < kV3Chunks) {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) p[i] = __ldg(pr + v3_chunk(ci + 1) * 16 + i);
+                    for (int i = 0; i < 8; i++) pn[i] = __ldg(pf + (v3_chunk(ci + 2) * 8 + i) * (4 * kTcDirs));
                 }
                 uint32_t hi[8], lo8[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    const float ph_hi = (i & 1) ? c[i >> 1].z : c[i >> 1].x;
-                    const float ph_lo = (i & 1) ? c[i >> 1].w : c[i >> 1].y;
-                    float t1 = __fmul_rn(bin, ph_hi);              // exact: bin < 2^10, ph_hi multiple of 2^-12
-                    t1 = __fsub_rn(t1, rintf(t1));
-                    const float fr = __fmaf_rn(bin, ph_lo, t1);
                     float sn, cs;
-                    sincospif(-2.0f * fr, &sn, &cs);
+                    if (dbg & 1) { sn = 0.25f; cs = 0.75f; } else phasor_fix(bin * c[i], cs, sn);
                     cs *= 256.0f; sn *= 256.0f;
                     const __half2 h = __floats2half2_rn(cs, sn);
                     const float2 hf = __half22float2(h);
@@ -668,8 +759,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) mvdr_tc_steer_kernel3(const uns
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x, w++) {
             const int f = unit / tiles, tile = unit - f * tiles;
             const int d = tile * kTcDirs + warp * 32 + lane;
-            const float4 *cs4 = (const float4 *)(colscale + (size_t)f * kTcRows);
-            float q = 0.0f;
+            const float sc = __ldg(colscale + f);          // per-bin scale 2^-(e+8), applied once to q
+            float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
             bfptx::mbar_wait(t0_done, w & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -678,19 +769,17 @@ __global__ void __launch_bounds__(kV3Threads, 1) mvdr_tc_steer_kernel3(const uns
                 float v[32];
                 tmem_ld32(lane_base + (uint32_t)c0, v);
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const float4 s4 = __ldg(cs4 + (c0 >> 2) + i);
-                    float x;
-                    x = v[4 * i] * s4.x;     q = fmaf(x, x, q);
-                    x = v[4 * i + 1] * s4.y; q = fmaf(x, x, q);
-                    x = v[4 * i + 2] * s4.z; q = fmaf(x, x, q);
-                    x = v[4 * i + 3] * s4.w; q = fmaf(x, x, q);
+                for (int i = 0; i < 8; i++) {                 // four independent chains
+                    q0 = fmaf(v[4 * i], v[4 * i], q0);
+                    q1 = fmaf(v[4 * i + 1], v[4 * i + 1], q1);
+                    q2 = fmaf(v[4 * i + 2], v[4 * i + 2], q2);
+                    q3 = fmaf(v[4 * i + 3], v[4 * i + 3], q3);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) bfptx::mbar_arrive(acc_free);
-            if (d < D) qout[(size_t)f * D + d] = q;
+            if (d < D) qout[(size_t)f * D + d] = ((q0 + q1) + (q2 + q3)) * (sc * sc);
         }
     }
     tc_fence_before();
@@ -710,6 +799,7 @@ __global__ void mvdr_tc_reduce_kernel(const float *__restrict__ q, int F, int D,
 }
 
 static DevBuf g_image, g_q, g_phi;
+static const uint32_t *g_phifix = nullptr;
 
 // reduced phase table of the generators (mvdr_tc_phi_kernel), rebuilt when the geometry changes
 static int ensure_phi(const double *d_u, int D, int M, double scale, cudaStream_t st)
@@ -737,8 +827,8 @@ int mvdr_steer_tc(const float2 *d_linv, const double *d_u, int M, int F, int lo,
     const int version = getenv("BF_MVDR_TC") ? atoi(getenv("BF_MVDR_TC")) : 3;
     if (version >= 3) {
         static DevBuf expo, colscale;
-        if ((rc = expo.ensure((size_t)F * kTcMics * sizeof(int)))) return rc;
-        if ((rc = colscale.ensure((size_t)F * kTcRows * sizeof(float)))) return rc;
+        if ((rc = expo.ensure((size_t)F * sizeof(int)))) return rc;
+        if ((rc = colscale.ensure((size_t)F * sizeof(float)))) return rc;
         mvdr_tc_rowscale_kernel<<<F, kTcMics, 0, st>>>(d_linv, expo.as<int>(), colscale.as<float>());
         BF_CHECK_LAUNCH();
         mvdr_tc_prep3_kernel<<<dim3(kV3Chunks, F), 256, 0, st>>>(d_linv, expo.as<int>(), g_image.as<unsigned char>());
@@ -748,10 +838,21 @@ int mvdr_steer_tc(const float2 *d_linv, const double *d_u, int M, int F, int lo,
         BF_CUDA(cudaFuncSetAttribute(mvdr_tc_steer_kernel3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int units = tiles * F;
         const int grid = units < state().sm_count ? units : state().sm_count;
-        if ((rc = ensure_phi(d_u, D, M, bin_hz * inv_c, st))) return rc;
-        if (lo + F > 1024) { set_error(BF_ERR_CONFIG, "tensor-core MVDR: bin index must stay below 1024"); return BF_ERR_CONFIG; }
-        mvdr_tc_steer_kernel3<<<grid, kV3Threads, smem, st>>>(g_image.as<unsigned char>(), g_phi.as<float2>(),
-                                                             colscale.as<float>(), F, lo, D, tiles, g_q.as<float>());
+        {   // fixed-point phase table, rebuilt when the geometry changes
+            static DevBuf fixbuf;
+            static uint64_t fix_gen = ~0ull; static double fix_scale = 0.0; static int fix_D = 0;
+            if (fix_gen != fd_geometry_generation() || fix_scale != bin_hz * inv_c || fix_D != D) {
+                const size_t cnt = (size_t)tiles * kTcMics * kTcDirs;
+                if ((rc = fixbuf.ensure(cnt * sizeof(uint32_t)))) return rc;
+                mvdr_tc_phifix_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_u, D, bin_hz * inv_c, tiles, fixbuf.as<uint32_t>());
+                BF_CHECK_LAUNCH();
+                fix_gen = fd_geometry_generation(); fix_scale = bin_hz * inv_c; fix_D = D;
+            }
+            g_phifix = fixbuf.as<uint32_t>();
+        }
+        const int dbg = getenv("BF_MVDR_DBG") ? atoi(getenv("BF_MVDR_DBG")) : 0;
+        mvdr_tc_steer_kernel3<<<grid, kV3Threads, smem, st>>>(g_image.as<unsigned char>(), g_phifix,
+                                                             colscale.as<float>(), F, lo, D, tiles, g_q.as<float>(), dbg);
         BF_CHECK_LAUNCH();
         mvdr_tc_reduce_kernel<<<(D + 255) / 256, 256, 0, st>>>(g_q.as<float>(), F, D, d_power);
         BF_CHECK_LAUNCH();

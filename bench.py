@@ -294,6 +294,57 @@ def mvdr_c4(nat, L, torch, stream, bins=512, dirs=32768, K=64):
                          "peak_source": "measured dense bf16 burst (MEASURED_PEAKS.json)"}}
 
 
+def mvdr_c4_sharded(torch, dist, nat, L, rank, world, bins=512, dirs=32768, K=64):
+    """BASELINE config C4 with the DIRECTIONS sharded over the ranks (FD path): every rank computes the
+    spectra, covariance, factor and inverse in full and steers dirs / world directions on the tcgen05 kernel;
+    the slices are exchanged with NVLink peer stores (lib.sharded.PeerGather, no NCCL on the data path).
+    Whole-job maps/s = 1 / (slowest rank's time per map, device-timed)."""
+    import realtime_scripts.calc_r_prime as rp
+    import realtime_scripts.config as cfg
+    from lib.sharded import PeerGather, fd_mvdr_sharded
+    M, N, F = 256, 1024, bins
+    res_x, res_y = 256, dirs // 256
+    D = res_x * res_y
+    pos_all, _ = rp.calc_r_prime(cfg.ELEMENT_DISTANCE)
+    x_max = np.tan(np.deg2rad(cfg.VIEW_ANGLE / 2))
+    xs = np.linspace(-x_max, x_max, res_x)
+    ys = np.linspace(-x_max / cfg.ASPECT_RATIO, x_max / cfg.ASPECT_RATIO, res_y)
+    act = np.arange(M, dtype=np.int32)
+    p = nat.ptr
+    mx, my = np.ascontiguousarray(pos_all[0]), np.ascontiguousarray(pos_all[1])
+    nat.check(L.bf_fd_setup(M, N, 48828.0, 343.0, 1, 1 + F, p(xs), res_x, p(ys), res_y, 1.0, p(mx), p(my), p(act), M))
+    gen = torch.Generator(device="cuda").manual_seed(1237)          # same seed on every rank: same snapshots
+    snaps = 0.05 * torch.randn((K, M, N), generator=gen, device="cuda")
+    t = torch.arange(N, device="cuda")[None, None, :]
+    m = torch.arange(M, device="cuda")[None, :, None]
+    for f0, amp, slope in ((2000.0, 0.3, 0.011), (5000.0, 0.2, -0.023), (9000.0, 0.1, 0.005)):
+        snaps += amp * torch.sin(2 * np.pi * f0 * (t + slope * m * 48.828) / 48828.0)
+    snaps = snaps.float().contiguous()
+    peer = PeerGather(D, 1, rank, world, dist, depth=2)
+    times = []
+    for i in range(4):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        a.record()
+        fd_mvdr_sharded(peer, i, snaps, K, 1e-2)
+        peer.ready(i)
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    peer.check()
+    power = peer.maps(3).reshape(-1)
+    finite = bool(torch.isfinite(power).all())
+    tt = torch.tensor([float(np.mean(times[1:]))], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    peer.close()
+    ms = float(tt[0])
+    return {"workload": "C4 sharded: FD-MVDR, 256 mics, 1024-pt FFT, %d bins, K=%d, %d directions over %d GPUs "
+                        "(%d each), slices exchanged by NVLink peer stores" % (F, K, D, world, (D + world - 1) // world),
+            "maps_per_s": 1e3 / ms, "ms_per_map": ms, "finite": finite, "n_gpus": world}
+
+
 def replay_c5_sharded_local(torch, nat, algo, d_mics, n, D, M, N, rank):
     """C5 across GPUs, this rank's part: its own 20 s recording (recording id = rank, seed 1238 + id) replayed
     entirely on its GPU (recordings shard with no collective).  Returns (frames, ms); no collective in here."""
@@ -315,6 +366,47 @@ def replay_c5_sharded_local(torch, nat, algo, d_mics, n, D, M, N, rank):
     b.record()
     torch.cuda.synchronize()
     return total, a.elapsed_time(b)
+
+
+def replay_c5_stream(torch, nat, algo, d_mics, n, M, rank, minutes=None):
+    """BASELINE config C5 for real: one HOUR of the 256-channel stream as the Zybo sends it (int32 datagram
+    payloads, 1 KiB per sample instant = 180 GB) goes host -> device through pinned double-buffered copies and on
+    through wire-format conversion -> 30 fps windows -> C3 power maps -> 640x360 overlay + peak + confidence
+    (lib.replay.stream_video), H2D inside the timing.  Host memory holds `minutes` of recording (BF_C5_MINUTES,
+    default 4 = 11.7 GB pinned; seed 1238 + recording id = rank) and is replayed 60 / minutes times, so the
+    bytes crossing PCIe are the full hour's; nothing but two chunks (2 x 0.43 GB) is resident on the GPU."""
+    from lib import replay
+    if minutes is None:
+        minutes = float(os.environ.get("BF_C5_MINUTES", "4"))
+    if minutes <= 0:
+        return None
+    fs = 48828
+    total = int(minutes * 60 * fs)
+    h = torch.empty((total, M), dtype=torch.int32, pin_memory=True)
+    gen = torch.Generator(device="cuda").manual_seed(1238 + rank)
+    piece = 1 << 20
+    tone = torch.arange(M, device="cuda", dtype=torch.float32)[None, :] * 0.37
+    for off in range(0, total, piece):
+        c = min(piece, total - off)
+        t = torch.arange(off, off + c, device="cuda", dtype=torch.float32)[:, None]
+        x = 0.02 * torch.randn((c, M), generator=gen, device="cuda") + 0.05 * torch.sin(2 * np.pi * 3000.0 / fs * t + tone)
+        h[off:off + c].copy_((x * 8388608.0).to(torch.int32))
+    torch.cuda.synchronize()
+    stream_minutes = float(os.environ.get("BF_C5_STREAM_MINUTES", "60"))     # tests shorten the hour
+    passes = max(1, int(round(stream_minutes / minutes)))
+    warm = replay.stream_video(h[:10 * fs], 4, algo, d_mics, n, chunk_frames=256)           # warm-up: 10 s of stream
+    res = replay.stream_video(h, 4, algo, d_mics, n, chunk_frames=256, passes=passes)
+    info = res["info"].numpy().view(nat.HEAT_INFO_DTYPE)
+    out = {"frames": res["frames"], "seconds": res["seconds"], "frames_per_s": res["frames_per_s"],
+           "x_realtime_at_30fps": res["frames_per_s"] / 30.0, "stream_seconds": res["frames"] / 30.0,
+           "host_recording_minutes": minutes, "passes": passes, "h2d_gb": res["h2d_bytes"] / 1e9,
+           "pcie_h2d_gb_per_s": res["h2d_gb_per_s"],
+           "stage_ms": res["stage_ms"], "stage_note": "device time per stage summed over chunks; h2d runs on the copy "
+                                                      "stream under the compute of the previous chunk",
+           "overlay_fraction": float(np.mean(info["overlay"] != 0)), "mean_confidence": float(res["confidence"].mean()),
+           "warmup_frames": warm["frames"]}
+    del h
+    return out
 
 
 def replay_c5(args, nat, torch, algo, d_mics, n, D, M, N):
@@ -432,6 +524,63 @@ def miso_c2(args, nat, L, config, directions, torch, stream, hbm_peak):
                                   "traffic": _traffic("miso_stream_%s_%d" % (name, blocks))}}
     del sig, out
     return res
+
+def _percentiles(ns):
+    a = np.sort(np.asarray(ns, np.float64)) / 1e3
+    return {"p50_us": float(a[len(a) // 2]), "p99_us": float(a[min(len(a) - 1, int(len(a) * 0.99))]),
+            "min_us": float(a[0]), "max_us": float(a[-1]), "calls": int(len(a))}
+
+
+def live_latency(nat, L, config, directions):
+    """Per-call latency of the two LIVE surfaces of the reference, through the C ABI with pageable host buffers
+    (what a maintainer gets by swapping the library under PC/src/main.pyx):
+      mimo_pad(signals, image, adaptive_array, n)   one power map per 256-sample buffer -- the producer loops
+                                                    (main.pyx:554-579) call it once per 5.24 ms buffer
+      miso_steer_listen(out, adaptive_array, n, o)  one block of beam audio (api.c:491-543, miso_loop): get_data
+                                                    from the registered source -> delay-and-sum -> host
+    at the reference's stock configuration (256 mics, 57x32 grid) and at C3's 180x180 grid for mimo_pad.
+    Wall clock per call (time.perf_counter_ns), after warm-up; budget = one buffer period = 5243 us."""
+    from lib import beamformer, synthetic
+    out = {"budget_us_per_buffer": 1e6 * 256 / 48828.0}
+    for name, rx, ry in (("stock_57x32", 57, 32), ("c3_180x180", 180, 180)):
+        config.reload(N_MICROPHONES=256, N_SAMPLES=256, MAX_RES_X=rx, MAX_RES_Y=ry, N_TAPS=8, SKIP_N_MICS=1,
+                      GEOMETRY_N_MICS=256, GEOMETRY_N_ARRAYS=4)
+        nat.configure_from(config)
+        directions.load_pad_from_geometry()
+        mics, n = directions.active_microphones()
+        mics = nat.i32(mics)
+        D = rx * ry
+        sig = np.ascontiguousarray(synthetic.plot_py_stimulus(256, 256))
+        img = np.zeros(D, np.float32)
+        for _ in range(20):
+            L.mimo_pad(nat.ptr(sig), nat.ptr(img), nat.ptr(mics), n)
+        nat.check()
+        ts = []
+        for _ in range(300):
+            t0 = time.perf_counter_ns()
+            L.mimo_pad(nat.ptr(sig), nat.ptr(img), nat.ptr(mics), n)
+            ts.append(time.perf_counter_ns() - t0)
+        nat.check()
+        out["mimo_pad_" + name] = _percentiles(ts)
+        if name == "stock_57x32":
+            beamformer.connect(False, verbose=False, source=beamformer.ArraySource(np.tile(sig, (1, 8))))
+            try:
+                beam = np.zeros(256, np.float32)
+                off = (16 * 57 + 28) * n
+                for _ in range(20):
+                    L.miso_steer_listen(nat.ptr(beam), nat.ptr(mics), n, off)
+                nat.check()
+                ts = []
+                for _ in range(500):
+                    t0 = time.perf_counter_ns()
+                    L.miso_steer_listen(nat.ptr(beam), nat.ptr(mics), n, off)
+                    ts.append(time.perf_counter_ns() - t0)
+                nat.check()
+                out["miso_steer_listen_" + name] = _percentiles(ts)
+            finally:
+                beamformer.disconnect()
+    return out
+
 
 def fir_default(nat, L, config, torch, stream, clocks):
     """FIR (fractional-delay filter) power maps at the reference's stock configuration: 57x32 grid, 256
@@ -763,7 +912,7 @@ def main():
                 "fp32_frac_of_148x128_lanes": (adds / (k_ms * 1e-3)) / fp32_peak if fp32_peak else None}
 
     # ---- e2e: the reference-facing call with host buffers -------------------------------------
-    e2e, miso, mvdr, replay, heat, fir = None, None, None, None, None, None
+    e2e, miso, mvdr, replay, heat, fir, latency = None, None, None, None, None, None, None
     if not args.no_extras:
         # (1) the drop-in per-buffer call: mimo_pad(signals, image, adaptive_array, n), pageable host
         #     memory, one map per call, synchronous (what PC/src/main.pyx loops do per frame)
@@ -820,9 +969,14 @@ def main():
         # ---- extra: BASELINE config C5 (bounded sample), then C2 and C4 -----------------------
         if world > 1 and args.workload == "c3":
             frames_r, ms_r, err_r = 0, 0.0, None
+            stream_r = None
             try:
                 dist.barrier()
-                frames_r, ms_r = replay_c5_sharded_local(torch, nat, algo, d_mics, n, D, M, N, rank)
+                stream_r = replay_c5_stream(torch, nat, algo, d_mics, n, M, rank)
+                if stream_r is not None:
+                    frames_r, ms_r = stream_r["frames"], 1e3 * stream_r["seconds"]
+                else:
+                    frames_r, ms_r = replay_c5_sharded_local(torch, nat, algo, d_mics, n, D, M, N, rank)
             except Exception as e:  # noqa: BLE001
                 err_r = str(e)
             tr = torch.tensor([ms_r, float(frames_r), 0.0 if err_r is None else 1.0], device="cuda", dtype=torch.float64)
@@ -833,14 +987,29 @@ def main():
                 replay = {"error": err_r or "a peer rank failed"}
             else:
                 fps_all = float(tr[1]) / (float(tmax[0]) * 1e-3)
-                replay = {"workload": "C5 sharded: %d recordings of 20 s (one per GPU, 1.0 GB each, resident), 30 fps video, "
-                                      "180x180 maps, %d frames in total, no collective" % (world, int(tr[1])),
-                          "frames_per_s": fps_all, "x_realtime_at_30fps": fps_all / 30.0, "ms": float(tmax[0])}
+                if stream_r is not None:
+                    replay = {"workload": "C5 sharded: %d one-hour recordings in the wire format (one per GPU, streamed from "
+                                          "pinned host memory: %.0f min resident x %d passes each), 30 fps video, 180x180 maps, "
+                                          "640x360 overlay, %d frames in total, no collective"
+                                          % (world, stream_r["host_recording_minutes"], stream_r["passes"], int(tr[1])),
+                              "frames_per_s": fps_all, "x_realtime_at_30fps": fps_all / 30.0, "ms": float(tmax[0]),
+                              "rank0": stream_r}
+                else:
+                    replay = {"workload": "C5 sharded: %d recordings of 20 s (one per GPU, 1.0 GB each, resident), 30 fps "
+                                          "video, 180x180 maps, %d frames in total, no collective" % (world, int(tr[1])),
+                              "frames_per_s": fps_all, "x_realtime_at_30fps": fps_all / 30.0, "ms": float(tmax[0])}
         elif rank == 0 and args.workload == "c3":
             try:
                 replay = replay_c5(args, nat, torch, algo, d_mics, n, D, M, N)
+                replay["one_hour_stream"] = replay_c5_stream(torch, nat, algo, d_mics, n, M, 0)
             except Exception as e:  # noqa: BLE001
                 replay = {"error": str(e)}
+        mvdr_sh = None
+        if world > 1 and peer is not None:               # every rank: direction-sharded C4 (peer memory available)
+            try:
+                mvdr_sh = mvdr_c4_sharded(torch, dist, nat, L, rank, world)
+            except Exception as ex:  # noqa: BLE001
+                mvdr_sh = {"error": str(ex)}
         if rank == 0 and args.workload == "c3":
             try:
                 hm = d_maps if (world == 1 or peer) else d_maps[:D].t().contiguous()   # [F][D] maps of the last step
@@ -856,10 +1025,16 @@ def main():
                 mvdr = mvdr_c4(nat, L, torch, stream)
             except Exception as e:  # noqa: BLE001
                 mvdr = {"error": str(e)}
+            if mvdr_sh is not None and isinstance(mvdr, dict):
+                mvdr["sharded"] = mvdr_sh
             try:
                 fir = fir_default(nat, L, config, torch, stream, clocks)
             except Exception as e:  # noqa: BLE001
                 fir = {"error": str(e)}
+            try:
+                latency = live_latency(nat, L, config, directions)
+            except Exception as e:  # noqa: BLE001
+                latency = {"error": str(e)}
 
     if rank == 0:
         line = {
@@ -876,6 +1051,7 @@ def main():
                        "exact_sum": args.exact_sum},
             "sum_step_ms": dev_ms, "wall_s": t_wall, "gather_note": gather_note, "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "miso": miso, "mvdr": mvdr, "replay": replay, "heatmap": heat, "fir": fir,
+            "latency": latency,
             # last on purpose: the tail of the line is what a truncated log keeps
             "e2e_sharded_maps_per_s": (e2e or {}).get("sharded", {}).get("value") if isinstance((e2e or {}).get("sharded"), dict) else None,
             "gather_check": gather_check,

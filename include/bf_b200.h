@@ -223,6 +223,16 @@ int bf_fd_das_dev(const float *d_signals, float *d_heatmap, int frames, float th
  * 1 / Re(a^H R_f^-1 a), R_f = 1/K sum_k x_k x_k^H + loading * tr(R_f)/M * I. */
 int bf_fd_mvdr(const float *snapshots, float *power, int K, double loading);
 int bf_fd_mvdr_dev(const float *d_snapshots, float *d_power, int K, double loading, void *stream);
+/* Direction-sharded frequency-domain maps ("FD path: shard directions"): only directions
+ * [d_begin, d_begin + d_count) of the grid are steered -- d_power is float [d_count] (MVDR) or
+ * [frames][d_count] un-normalised (DAS).  Spectra, covariance, factor and inverse are computed in full on every
+ * rank (0.5 % of the work).  bf_peer_scatter / PeerGather assemble the slices; bf_fd_normalise_dev applies the
+ * reference's P / max(P) (or all zeros below the threshold) to an assembled [frames][D] map. */
+int bf_fd_mvdr_dev_slice(const float *d_snapshots, float *d_power, int K, double loading, int d_begin,
+                         int d_count, void *stream);
+int bf_fd_das_dev_slice(const float *d_signals, float *d_power, int frames, int d_begin, int d_count,
+                        void *stream);
+int bf_fd_normalise_dev(float *d_heatmap, int frames, float threshold, int normalise, void *stream);
 /* device milliseconds of the stages of the last MVDR call: FFT, covariance + loading, Cholesky,
  * triangular inverse, steering contraction */
 int bf_fd_mvdr_timings(float *ms5);
@@ -249,6 +259,13 @@ typedef struct bf_datagram_header {
  * d_zero_mask optional uint8[n_channels]: channels to clear (api.c:835-858), or NULL */
 int bf_ingest_dev(const int *d_stream, float *d_signals, int frames, int n_arrays, int rows, int cols,
                   double norm, int quirk, const unsigned char *d_zero_mask, void *stream);
+/* Batch replay of a stored stream (BASELINE config C5): frame f is the n_samples-datagram WINDOW that begins at
+ * datagram d_starts[f] (device int64 [frames], e.g. floor(k*fs/fps)) of d_stream, device int32
+ * [total_datagrams][n_microphones]; datagrams beyond the end read as silence.  Same conversion as
+ * bf_ingest_dev -- the window gather and the wire-format conversion in one pass. */
+int bf_ingest_windows_dev(const int *d_stream, long total_datagrams, const long *d_starts, float *d_signals,
+                          int frames, int n_arrays, int rows, int cols, double norm, int quirk,
+                          const unsigned char *d_zero_mask, void *stream);
 
 /* ---- window gather for batch replay (BASELINE config C5) ---------------------------------
  * d_recording device float [n_microphones][samples] (PC/record.py .npy layout), d_starts device
@@ -285,6 +302,11 @@ int bf_mimo_dev_gather_sync(int algo, const float *d_signals, int frames, const 
 int bf_gather_signal(void *const *flag_arrays /* host array of `world` device pointers */, int world, int rank,
                      long long step, void *stream);
 int bf_gather_wait(const void *d_my_flags, int world, long long step, int *d_timed_out, void *stream);
+/* Device-side all-gather of a finished slice: d_src float [frames][count] -> slice `rank` of every rank's gather
+ * buffer float [world][frames][per_rank] (peer stores over NVLink).  For producers that do not store to the
+ * peers themselves (the frequency-domain maps); follow it with bf_gather_signal. */
+int bf_peer_scatter(const float *d_src, long count, int frames, int rank, int world, void *const *gather_bufs,
+                    long per_rank, void *stream);
 
 /* ---- heat-map post-processing (SURVEY 8f "next" #2) -----------------------------------------
  * The step after the beamformer: PC/src/visual.py:130-171 calculate_heatmap (log scale),

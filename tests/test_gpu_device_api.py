@@ -325,6 +325,50 @@ def test_wire_format_ingest_vs_oracle(quirk):
     assert L.bf_ingest_dev(d_in.data_ptr(), d_out.data_ptr(), 1, 4, 8, 8, 1000.0, 1, None, None) != 0   # not 2^k
 
 
+def test_streaming_replay_of_a_wire_format_recording():
+    """BASELINE config C5 as a stream (lib.replay.stream_video): a stored recording of datagram payloads in pinned
+    host memory -> chunked double-buffered H2D -> windowed wire-format conversion (bf_ingest_windows_dev) ->
+    power maps -> overlay.  At C1 size against the oracle chain: every 30 fps frame == orc_ingest of its
+    256-datagram window (reference quirk included) followed by the oracle's mimo_pad, bit for bit, with chunk
+    boundaries that cut between frames, two passes, and frames sharded 2 ways."""
+    import ctypes
+    from oracle import cpu
+    config, nat, L = _setup("c1")
+    torch = _torch()
+    from lib import directions, replay
+    g = gold("c1")
+    mics = nat.i32(g["mic_ids"])
+    D, n, N, M = 400, 64, 256, 64
+    whole, _ = directions.whole_and_f32()
+    L.load_coefficients_pad(nat.ptr(whole), whole.size)
+    nat.check()
+    rng = np.random.default_rng(77)
+    total = 20000                                                    # 13 frames at 30 fps
+    stream = rng.integers(-(1 << 23), 1 << 23, (total, M)).astype(np.int32)
+    h_stream = torch.from_numpy(stream).pin_memory()
+    d_mics = torch.from_numpy(mics).cuda()
+    starts = replay.frame_starts(replay.n_frames_in(total))
+    want = []
+    for s0 in starts:
+        sig = np.zeros((M, N), np.float32)
+        win = np.ascontiguousarray(stream[s0:s0 + N])
+        cpu.lib().orc_ingest(win.ctypes.data_as(ctypes.c_void_p), sig.ctypes.data_as(ctypes.c_void_p), N, M, 1, 8, 8,
+                             ctypes.c_double(2.0 ** 24), 1)
+        want.append(cpu.mimo_pad(sig, mics, whole, D))
+    want = np.stack(want)
+    res = replay.stream_video(h_stream, 1, nat.ALGO_PAD, d_mics, n, chunk_frames=5, passes=2, keep_maps=True,
+                              window=(64, 36))
+    assert res["frames"] == 2 * len(starts) and res["recording_frames"] == len(starts)
+    assert bits_equal(res["maps"].cpu().numpy(), want)
+    # every chunk copies the datagrams from its first window to the end of its last one, once per pass
+    per_pass = sum(int(starts[min(a + 5, len(starts)) - 1] + N - starts[a]) for a in range(0, len(starts), 5))
+    assert res["h2d_bytes"] == 2 * per_pass * M * 4 and res["confidence"].shape[0] == 2 * len(starts)
+    assert torch.equal(res["confidence"][:len(starts)], res["confidence"][len(starts):])          # same content twice
+    odd = replay.stream_video(h_stream, 1, nat.ALGO_PAD, d_mics, n, chunk_frames=4, first_frame=1, frame_step=2,
+                              keep_maps=True, overlay=False)
+    assert bits_equal(odd["maps"].cpu().numpy(), want[1::2])
+
+
 def test_batch_replay_windows_and_maps():
     """BASELINE config C5 mechanics at C1 size: 30 fps windows at floor(k*fs/30) of a channel-major
     recording -> gather kernel -> batched maps == one mimo_pad call per NumPy-sliced window."""

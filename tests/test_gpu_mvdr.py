@@ -109,3 +109,32 @@ def test_mvdr_rejects_singular_covariance():
     P = np.zeros(169, np.float32)
     assert L.bf_fd_mvdr(nat.ptr(snaps), nat.ptr(P), 2, 0.0) != 0        # K < M and no loading
     assert b"positive definite" in L.bf_last_error()
+
+
+def test_direction_slices_equal_the_full_map():
+    """Direction sharding of the frequency-domain maps (FD path) on one GPU: steering only a slice
+    of the grid (bf_fd_mvdr_dev_slice / bf_fd_das_dev_slice) gives exactly the values of the full map, whatever
+    the slice boundaries (they cut through the 128-direction MMA tile)."""
+    import torch
+    g = gold("fd_das")
+    bfa, nat, L = _setup()
+    K, D = 6, 169
+    snaps = torch.from_numpy(_snapshots(g, K, 9)).cuda()
+    full = torch.zeros(D, device="cuda")
+    nat.check(L.bf_fd_mvdr_dev(snaps.data_ptr(), full.data_ptr(), K, 1e-2, None))
+    das = torch.zeros((2, D), device="cuda")
+    nat.check(L.bf_fd_das_dev(snaps.data_ptr(), das.data_ptr(), 2, 0.0, 0, None))
+    torch.cuda.synchronize()
+    for bounds in ((0, 100, 169), (0, 1, 128, 129, 169)):
+        parts, dparts = [], []
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            part = torch.full((b - a,), float("nan"), device="cuda")
+            nat.check(L.bf_fd_mvdr_dev_slice(snaps.data_ptr(), part.data_ptr(), K, 1e-2, a, b - a, None))
+            parts.append(part)
+            dp = torch.full((2, b - a), float("nan"), device="cuda")
+            nat.check(L.bf_fd_das_dev_slice(snaps.data_ptr(), dp.data_ptr(), 2, a, b - a, None))
+            dparts.append(dp)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat(parts), full), bounds
+        assert torch.equal(torch.cat(dparts, dim=1), das), bounds
+    assert L.bf_fd_mvdr_dev_slice(snaps.data_ptr(), full.data_ptr(), K, 1e-2, 100, 100, None) != 0     # beyond the grid

@@ -196,11 +196,20 @@ int fd_setup(int n_mics, int n_samples, double fs, double c, int lo_bin, int hi_
     return BF_OK;
 }
 
+// d_count < 0: the whole grid, normalised per the reference; otherwise the un-normalised power of directions
+// [d_begin, d_begin + d_count) as float [frames][d_count] (direction-sharded runs normalise after the gather).
 int fd_das_dev(const float *d_signals, float *d_heat, int frames, float threshold, int normalise,
-               cudaStream_t st)
+               cudaStream_t st, int d_begin = 0, int d_count = -1)
 {
     FdState &G = g_fd;
     if (G.D == 0) { set_error(BF_ERR_NOT_LOADED, "fd: bf_fd_setup() has not been called"); return BF_ERR_NOT_LOADED; }
+    const bool slice = d_count >= 0;
+    if (slice && (d_begin < 0 || d_count < 1 || d_begin + d_count > G.D)) {
+        set_error(BF_ERR_ARG, "fd: direction slice [%d,+%d) outside the %d-direction grid", d_begin, d_count, G.D);
+        return BF_ERR_ARG;
+    }
+    const int Dn = slice ? d_count : G.D;
+    const double *u = G.u.as<double>() + (size_t)(slice ? d_begin : 0) * G.n_active;
     const int F = G.hi - G.lo;
     int rc = G.spec.ensure((size_t)frames * F * G.n_active * sizeof(float2));
     if (rc) return rc;
@@ -212,12 +221,24 @@ int fd_das_dev(const float *d_signals, float *d_heat, int frames, float threshol
     constexpr int TD = 64;
     // bin spacing of the reference's frequency axis: int(fs/2) / (N/2)
     const double bin_hz = (double)(int)((int)G.fs / 2) / (double)(G.N / 2);
-    fd_steer_kernel<TD><<<dim3((G.D + TD - 1) / TD, frames), TD, G.n_active * sizeof(float2), st>>>(
-        G.spec.as<float2>(), G.u.as<double>(), G.n_active, F, G.lo, bin_hz, 1.0 / G.c, G.D, d_heat);
+    fd_steer_kernel<TD><<<dim3((Dn + TD - 1) / TD, frames), TD, G.n_active * sizeof(float2), st>>>(
+        G.spec.as<float2>(), u, G.n_active, F, G.lo, bin_hz, 1.0 / G.c, Dn, d_heat);
     BF_CHECK_LAUNCH();
+    if (!slice) {
+        fd_norm_kernel<<<frames, 256, 0, st>>>(d_heat, G.D, threshold, normalise);
+        BF_CHECK_LAUNCH();
+    }
+    count_launch(slice ? 2 : 3);
+    return BF_OK;
+}
+
+int fd_normalise_dev(float *d_heat, int frames, float threshold, int normalise, cudaStream_t st)
+{
+    FdState &G = g_fd;
+    if (G.D == 0) { set_error(BF_ERR_NOT_LOADED, "fd: bf_fd_setup() has not been called"); return BF_ERR_NOT_LOADED; }
     fd_norm_kernel<<<frames, 256, 0, st>>>(d_heat, G.D, threshold, normalise);
     BF_CHECK_LAUNCH();
-    count_launch(3);
+    count_launch();
     return BF_OK;
 }
 
@@ -267,6 +288,24 @@ int bf_fd_das_dev(const float *d_signals, float *d_heatmap, int frames, float th
     if (rc) return rc;
     if (!d_signals || !d_heatmap || frames < 1) { set_error(BF_ERR_ARG, "bf_fd_das_dev: bad arguments"); return BF_ERR_ARG; }
     return fd_das_dev(d_signals, d_heatmap, frames, threshold, normalise, (cudaStream_t)stream);
+}
+
+int bf_fd_das_dev_slice(const float *d_signals, float *d_power, int frames, int d_begin, int d_count, void *stream)
+{
+    clear_error();
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!d_signals || !d_power || frames < 1) { set_error(BF_ERR_ARG, "bf_fd_das_dev_slice: bad arguments"); return BF_ERR_ARG; }
+    return fd_das_dev(d_signals, d_power, frames, 0.0f, 0, (cudaStream_t)stream, d_begin, d_count);
+}
+
+int bf_fd_normalise_dev(float *d_heatmap, int frames, float threshold, int normalise, void *stream)
+{
+    clear_error();
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!d_heatmap || frames < 1) { set_error(BF_ERR_ARG, "bf_fd_normalise_dev: bad arguments"); return BF_ERR_ARG; }
+    return fd_normalise_dev(d_heatmap, frames, threshold, normalise, (cudaStream_t)stream);
 }
 
 }  // extern "C"

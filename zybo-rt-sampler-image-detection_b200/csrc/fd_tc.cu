@@ -841,12 +841,13 @@ int mvdr_steer_tc(const float2 *d_linv, const double *d_u, int M, int F, int lo,
         {   // fixed-point phase table, rebuilt when the geometry changes
             static DevBuf fixbuf;
             static uint64_t fix_gen = ~0ull; static double fix_scale = 0.0; static int fix_D = 0;
-            if (fix_gen != fd_geometry_generation() || fix_scale != bin_hz * inv_c || fix_D != D) {
+            static const double *fix_u = nullptr;                  // a direction slice starts at another row of u
+            if (fix_gen != fd_geometry_generation() || fix_scale != bin_hz * inv_c || fix_D != D || fix_u != d_u) {
                 const size_t cnt = (size_t)tiles * kTcMics * kTcDirs;
                 if ((rc = fixbuf.ensure(cnt * sizeof(uint32_t)))) return rc;
                 mvdr_tc_phifix_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_u, D, bin_hz * inv_c, tiles, fixbuf.as<uint32_t>());
                 BF_CHECK_LAUNCH();
-                fix_gen = fd_geometry_generation(); fix_scale = bin_hz * inv_c; fix_D = D;
+                fix_gen = fd_geometry_generation(); fix_scale = bin_hz * inv_c; fix_D = D; fix_u = d_u;
             }
             g_phifix = fixbuf.as<uint32_t>();
         }

@@ -19,14 +19,20 @@
 
 namespace bf {
 
+// starts == NULL: frame f is the block of N consecutive datagrams f*N .. f*N+N-1 (what the receiver hands over);
+// otherwise frame f is the N-sample WINDOW that begins at datagram starts[f] of a stream of `total` datagrams
+// (batch replay: video frame k looks at floor(k*fs/fps), any offset); datagrams beyond `total` read as silence.
 __global__ void ingest_kernel(const int *__restrict__ stream, float *__restrict__ out, int N,
                               int n_mics_total, int n_channels, int rows, int cols, double inv_norm,
-                              int quirk, const unsigned char *__restrict__ zero_mask)
+                              int quirk, const unsigned char *__restrict__ zero_mask,
+                              const long *__restrict__ starts, long total)
 {
     __shared__ float tile[32][33];
     const int frame = blockIdx.z;
     const int s0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
-    const int *in = stream + (size_t)frame * N * n_mics_total;
+    const long first = starts ? starts[frame] : (long)frame * N;
+    const int *in = stream + (size_t)first * n_mics_total;
+    const long avail = starts ? total - first : (long)N;          // datagrams readable from `first` on
     float *o = out + (size_t)frame * n_mics_total * N;
     // load: thread (x = channel within tile, y = step within tile, 4 passes of 8 steps)
     const int s = s0 + threadIdx.x;
@@ -41,7 +47,7 @@ __global__ void ingest_kernel(const int *__restrict__ stream, float *__restrict_
     for (int k = threadIdx.y; k < 32; k += blockDim.y) {
         const int step = t0 + k;
         float v = 0.0f;
-        if (step < N && src >= 0) v = __double2float_rn(__dmul_rn((double)in[(size_t)step * n_mics_total + src], inv_norm));
+        if (step < N && step < avail && first + step >= 0 && src >= 0) v = __double2float_rn(__dmul_rn((double)in[(size_t)step * n_mics_total + src], inv_norm));
         tile[k][threadIdx.x] = v;
     }
     __syncthreads();
@@ -56,7 +62,8 @@ __global__ void ingest_kernel(const int *__restrict__ stream, float *__restrict_
 }
 
 int ingest_dev(const int *d_stream, float *d_out, int frames, int n_arrays, int rows, int cols, double norm,
-               int quirk, const unsigned char *d_zero_mask, cudaStream_t st)
+               int quirk, const unsigned char *d_zero_mask, cudaStream_t st, const long *d_starts = nullptr,
+               long total = 0)
 {
     State &S = state();
     const int N = S.cfg.n_samples, M = S.cfg.n_microphones;
@@ -68,7 +75,7 @@ int ingest_dev(const int *d_stream, float *d_out, int frames, int n_arrays, int 
     // norm is a power of two in the reference (2^24): multiplying by 1/norm is exact division
     dim3 grid((N + 31) / 32, (n_channels + 31) / 32, frames), block(32, 8);
     ingest_kernel<<<grid, block, 0, st>>>(d_stream, d_out, N, M, n_channels, rows, cols, 1.0 / norm, quirk,
-                                          d_zero_mask);
+                                          d_zero_mask, d_starts, total);
     BF_CHECK_LAUNCH();
     count_launch();
     return BF_OK;
@@ -90,6 +97,23 @@ extern "C" int bf_ingest_dev(const int *d_stream, float *d_signals, int frames, 
     frac = frexp(norm, &e);
     if (frac != 0.5) { set_error(BF_ERR_ARG, "bf_ingest_dev: NORM_FACTOR must be a power of two (got %g)", norm); return BF_ERR_ARG; }
     return ingest_dev(d_stream, d_signals, frames, n_arrays, rows, cols, norm, quirk, d_zero_mask, (cudaStream_t)stream);
+}
+
+extern "C" int bf_ingest_windows_dev(const int *d_stream, long total_datagrams, const long *d_starts, float *d_signals,
+                                     int frames, int n_arrays, int rows, int cols, double norm, int quirk,
+                                     const unsigned char *d_zero_mask, void *stream)
+{
+    clear_error();
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!d_stream || !d_starts || !d_signals || frames < 1 || total_datagrams < 1) {
+        set_error(BF_ERR_ARG, "bf_ingest_windows_dev: bad arguments");
+        return BF_ERR_ARG;
+    }
+    int e = 0;
+    if (frexp(norm, &e) != 0.5) { set_error(BF_ERR_ARG, "bf_ingest_windows_dev: NORM_FACTOR must be a power of two (got %g)", norm); return BF_ERR_ARG; }
+    return ingest_dev(d_stream, d_signals, frames, n_arrays, rows, cols, norm, quirk, d_zero_mask, (cudaStream_t)stream,
+                      d_starts, total_datagrams);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -37,9 +37,52 @@ __global__ void gather_wait_kernel(const long long *flags, int world, long long 
     __threadfence_system();
 }
 
+// Device-side all-gather of a finished slice: src float [frames][count] -> slice `rank` of every rank's
+// gather buffer float [world][frames][per_rank] (own memory and, through CUDA IPC, the peers': plain global
+// stores over NVLink).  Used where the producing kernel does not store to the peers itself (the frequency-
+// domain maps); the time-domain kernel fuses these stores into its epilogue.
+struct ScatterPtrs { float *p[8]; };
+__global__ void peer_scatter_kernel(const float *__restrict__ src, long count, int frames, int rank, int world,
+                                    const ScatterPtrs bufs, long per_rank)
+{
+    const long total = count * frames;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long f = i / count, d = i - f * count;
+        const float v = src[i];
+        const long off = ((long)rank * frames + f) * per_rank + d;
+        for (int r = 0; r < world; r++) bufs.p[r][off] = v;
+    }
+}
+
 }  // namespace bf
 
 using namespace bf;
+
+extern "C" int bf_peer_scatter(const float *d_src, long count, int frames, int rank, int world,
+                               void *const *gather_bufs, long per_rank, void *stream)
+{
+    clear_error();
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!d_src || !gather_bufs || count < 0 || frames < 1 || world < 1 || world > 8 || rank < 0 || rank >= world ||
+        per_rank < count) {
+        set_error(BF_ERR_ARG, "bf_peer_scatter: bad arguments");
+        return BF_ERR_ARG;
+    }
+    if (count == 0) return BF_OK;
+    ScatterPtrs sp{};
+    for (int r = 0; r < world; r++) {
+        if (!gather_bufs[r]) { set_error(BF_ERR_ARG, "bf_peer_scatter: null buffer for rank %d", r); return BF_ERR_ARG; }
+        sp.p[r] = (float *)gather_bufs[r];
+    }
+    const long total = count * frames;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    peer_scatter_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_src, count, frames, rank, world, sp, per_rank);
+    BF_CHECK_LAUNCH();
+    count_launch();
+    return BF_OK;
+}
 
 extern "C" int bf_dev_alloc(size_t bytes, void **d_ptr)
 {

@@ -79,6 +79,7 @@ def lib():
     L.bf_fd_get_covariance.argtypes = [vp, cs]
     L.bf_ingest_dev.argtypes = [vp, vp, ci, ci, ci, ci, cd, ci, vp, vp]
     L.bf_window_dev.argtypes = [vp, ctypes.c_long, vp, ci, vp, vp]
+    L.bf_ingest_windows_dev.argtypes = [vp, ctypes.c_long, vp, vp, ci, ci, ci, ci, cd, ci, vp, vp]
     cf, cl = ctypes.c_float, ctypes.c_long
     cll = ctypes.c_longlong
     L.bf_dev_alloc.argtypes = [cs, ctypes.POINTER(vp)]
@@ -90,6 +91,10 @@ def lib():
     L.bf_mimo_dev_gather_sync.argtypes = [ci, vp, ci, vp, ci, ci, ci, ci, ci, vp, ctypes.c_long, vp, cll, cll, vp, vp]
     L.bf_gather_signal.argtypes = [vp, ci, ci, cll, vp]
     L.bf_gather_wait.argtypes = [vp, ci, cll, vp, vp]
+    L.bf_peer_scatter.argtypes = [vp, ctypes.c_long, ci, ci, ci, vp, ctypes.c_long, vp]
+    L.bf_fd_mvdr_dev_slice.argtypes = [vp, vp, ci, cd, ci, ci, vp]
+    L.bf_fd_das_dev_slice.argtypes = [vp, vp, ci, ci, ci, vp]
+    L.bf_fd_normalise_dev.argtypes = [vp, ci, ctypes.c_float, ci, vp]
     L.bf_kf_create.restype = vp
     L.bf_kf_destroy.argtypes = [vp]
     L.bf_kf_destroy.restype = None

@@ -217,6 +217,26 @@ class PeerGather:
                                             self.d_begin, self.d_count, self.rank, self.world, self._buf_arrays[k],
                                             self.per, self._flag_array, wait_seq, seq, self.timed_out.data_ptr(), st))
 
+    def scatter(self, i, d_slice, stream=None):
+        """Step i for a producer that does not store to the peers itself (the frequency-domain maps): d_slice is
+        this rank's finished slice, CUDA float32 [F][d_count].  Waits (on the stream) until the buffer's previous
+        contents have been consumed everywhere, stores the slice into every rank's buffer over NVLink and
+        publishes the step -- the same protocol as step()."""
+        nat, L = self.nat, self.L
+        st = stream if stream is not None else self.torch.cuda.current_stream().cuda_stream
+        self._seq += 1
+        seq = self._seq
+        self._seq_of[i] = seq
+        k = i % self.depth
+        wait_seq = max(0, seq - self.depth + 1 + self.consume_lag)
+        if wait_seq > 0:
+            nat.check(L.bf_gather_wait(self.flags[self.rank], self.world, wait_seq, self.timed_out.data_ptr(), st))
+        if self.d_count > 0:
+            assert tuple(d_slice.shape) == (self.F, self.d_count) and d_slice.is_contiguous()
+            nat.check(L.bf_peer_scatter(d_slice.data_ptr(), self.d_count, self.F, self.rank, self.world,
+                                        self._buf_arrays[k], self.per, st))
+        nat.check(L.bf_gather_signal(self._flag_array, self.world, self.rank, seq, st))
+
     def ready(self, i, stream=None):
         """Make the stream wait until every rank's slice of step i has arrived; returns the
         [world][F][per] view of that step."""
@@ -258,3 +278,32 @@ def assemble_peer_layout(buf, n_directions):
 def assemble_reference(slices, n_directions):
     """NumPy model of the gather: list of per-rank [per][F] arrays -> [D][F]."""
     return np.concatenate(slices, axis=0)[:n_directions]
+
+
+def fd_mvdr_sharded(peer, i, d_snapshots, K, loading, stream=None):
+    """Step i of a direction-sharded MVDR map (FD path): every rank computes spectra, covariance,
+    factor and inverse in full (0.5 % of the work) and steers only its slice of the directions; the slices are
+    exchanged through `peer` (PeerGather(D, 1, ...)).  Returns nothing; peer.maps(i) is the assembled [1][D] map."""
+    torch, nat, L = peer.torch, peer.nat, peer.L
+    st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+    part = torch.empty((1, max(peer.d_count, 1)), dtype=torch.float32, device="cuda")
+    if peer.d_count > 0:
+        nat.check(L.bf_fd_mvdr_dev_slice(d_snapshots.data_ptr(), part.data_ptr(), K, loading, peer.d_begin,
+                                         peer.d_count, st))
+    peer.scatter(i, part[:, :peer.d_count].contiguous() if peer.d_count else part[:, :0], st)
+
+
+def fd_das_sharded(peer, i, d_signals, threshold=0.2, normalise=True, stream=None):
+    """Step i of direction-sharded frequency-domain DAS for peer.F frames: every rank transforms all channels,
+    steers its slice, scatters it; the assembled [F][D] power is normalised like the reference after the
+    gather (beam_forming_algorithm.py:58-63).  Returns the normalised (or raw) [F][D] maps."""
+    torch, nat, L = peer.torch, peer.nat, peer.L
+    st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+    part = torch.empty((peer.F, max(peer.d_count, 1)), dtype=torch.float32, device="cuda")
+    if peer.d_count > 0:
+        part = torch.empty((peer.F, peer.d_count), dtype=torch.float32, device="cuda")
+        nat.check(L.bf_fd_das_dev_slice(d_signals.data_ptr(), part.data_ptr(), peer.F, peer.d_begin, peer.d_count, st))
+    peer.scatter(i, part, st)
+    maps = peer.maps(i).contiguous()
+    nat.check(L.bf_fd_normalise_dev(maps.data_ptr(), peer.F, float(threshold), 1 if normalise else 0, st))
+    return maps

@@ -95,11 +95,11 @@ _BARRIER = None          # inherited by the forked workers (cannot be pickled)
 
 
 def _cpu_worker(args):
-    kind, ref_cfg, algo, sig, mics, table, D, maps = args
+    kind, ref_cfg, algo, sig, mics, table, D, maps, lib = args
     barrier = _BARRIER
     if kind == "reference":
         from oracle import ref
-        R = ref.RefC(ref_cfg)
+        R = ref.RefC(ref_cfg, lib)
         import ctypes
         p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
         img = np.zeros(R.D, np.float32)
@@ -144,7 +144,24 @@ def cpu_setup(wl_name, algo):
     return kind, wl["ref_cfg"], sig, np.ascontiguousarray(mics, np.int32), np.ascontiguousarray(table), D, n
 
 
-def cpu_run(wl_name, algo, maps_per_core, cores=None, setup=None):
+_REF_HANDLES = []        # the reference's shared objects, opened in the PARENT too (the workers are forked from it)
+
+
+def reference_builds(ref_cfg, kind):
+    """Builds of the reference's C available on this host: always the portable one (-mavx2 -mfma, what the
+    container that has /root/reference compiled), plus the x86-64-v4 one where the CPU has AVX-512 -- the
+    reference's own flags say -march=native, so on such a host that is what its authors would get."""
+    if kind != "reference":
+        return ["port"]
+    import ctypes
+    from oracle import ref
+    libs = ["libref.so"] + (["libref_v4.so"] if ref.v4_available(ref_cfg) else [])
+    for lib in libs:
+        _REF_HANDLES.append(ctypes.CDLL(os.path.join(ref.ROOT, ref_cfg, lib)))
+    return libs
+
+
+def cpu_run(wl_name, algo, maps_per_core, cores=None, setup=None, lib="libref.so"):
     """maps/s of the CPU implementation with `cores` processes, each producing whole maps
     (the reference is single-threaded with process-global tables)."""
     kind, ref_cfg, sig, mics, table, D, n = setup or cpu_setup(wl_name, algo)
@@ -153,11 +170,11 @@ def cpu_run(wl_name, algo, maps_per_core, cores=None, setup=None):
     ctx = mp.get_context("fork")
     _BARRIER = ctx.Barrier(cores)
     with ctx.Pool(cores) as pool:
-        times = pool.map(_cpu_worker, [(kind, ref_cfg, algo, sig, mics, table, D, maps_per_core)] * cores,
+        times = pool.map(_cpu_worker, [(kind, ref_cfg, algo, sig, mics, table, D, maps_per_core, lib)] * cores,
                          chunksize=1)
     wall = max(times)
     return dict(maps_per_s=cores * maps_per_core / wall, seconds=wall, cores=cores, kind=kind,
-                maps=cores * maps_per_core, D=D, n=n)
+                maps=cores * maps_per_core, D=D, n=n, lib=lib)
 
 
 def run_reference(args):
@@ -170,12 +187,19 @@ def run_reference(args):
     D, n = setup[5], setup[6]
     N = wl["N_SAMPLES"]
     cores = os.cpu_count() or 1
-    # one step = one whole map per core (bounded sample of the F-frame step of the GPU arm)
-    total = 0.0
-    for i in range(args.warmup + args.steps):
-        r = cpu_run(args.workload, args.algo, 1, cores, setup)
-        if i >= args.warmup:
-            total += r["seconds"]
+    libs = reference_builds(setup[1], setup[0])
+    # one step = one whole map per core (bounded sample of the F-frame step of the GPU arm); every available
+    # build of the reference is timed, the line's value is the fastest
+    builds, total = {}, None
+    for lib in libs:
+        t = 0.0
+        for i in range(args.warmup + args.steps):
+            r = cpu_run(args.workload, args.algo, 1, cores, setup, lib)
+            if i >= args.warmup:
+                t += r["seconds"]
+        builds[lib] = cores * args.steps / t
+        if total is None or t < total:
+            total = t
     kind = r["kind"]
     maps = cores * args.steps
     value = maps / total
@@ -187,7 +211,10 @@ def run_reference(args):
         "gmac_per_s": value * D * n * N / 1e9,
         "config": {"workload": wl["desc"], "algo": args.algo, "directions": D, "mics": n, "samples": N},
         "cpu_baseline": {"value": value, "unit": "maps/s", "cores": cores, "kind": kind,
-                         "sample": "%d whole maps per step (one per host core), %d steps" % (cores, args.steps)},
+                         "sample": "%d whole maps per step (one per host core), %d steps" % (cores, args.steps),
+                         "builds_maps_per_s": builds,
+                         "builds_note": "libref.so = the reference's C with -O3 -mavx2 -mfma; libref_v4.so = -march=x86-64-v4 "
+                                        "(what its -march=native gives on an AVX-512 host), timed only where the CPU has it"},
         "e2e": {"value": value, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -614,24 +641,28 @@ def fir_default(nat, L, config, torch, stream, clocks):
     return res
 
 
-def e2e_sharded(torch, dist, nat, L, algo, d_pool, d_mics, n, D, F, M, N, rank, world, steps):
+def e2e_sharded(torch, dist, nat, L, algo, d_pool, d_mics, n, D, F, M, N, rank, world, steps, bounds=None):
     """End to end through the DIRECTION-SHARDED path (the partition `value` measures at N > 1): every step the
-    F frames of the batch are copied host -> device on every rank (each GPU has its own PCIe link; the host
-    batch is the same pinned buffer content on all ranks), each rank computes its direction slice with the
+    F frames of the batch go host -> device ONCE over PCIe, F / world of them on every rank (each GPU has its
+    own link), are all-gathered over NVLink so that every rank holds the whole batch (one NCCL all-gather of the
+    INPUT: the only exchange this path needs besides the maps), each rank computes its direction slice with the
     fused kernel + NVLink peer stores, and rank 0 copies the assembled [F][D] maps device -> host.  All copies
-    are inside the timed region; H2D of step i+1 and D2H of step i-1 overlap the kernel of step i (three
-    streams).  Returns maps/s (max over ranks) or None when peer memory is unavailable."""
-    from lib.sharded import PeerGather, assemble_peer_layout
+    are inside the timed region; H2D + input gather of step i+1 and D2H of step i-1 overlap the kernel of step i
+    (three streams).  Returns maps/s (max over ranks) or None when peer memory is unavailable."""
+    from lib.sharded import PeerGather
     try:
-        peer = PeerGather(D, F, rank, world, dist, depth=4, consume_lag=1)
+        peer = PeerGather(D, F, rank, world, dist, depth=4, consume_lag=1, bounds=bounds)
     except RuntimeError:
         return None
     frame_bytes = M * N * 4
     n_host = min(d_pool.shape[0], 3)
-    h_in = torch.empty((n_host, F, M, N), dtype=torch.float32).pin_memory()
-    h_in.copy_(d_pool[:n_host].cpu())
+    split = F % world == 0                      # otherwise every rank copies the whole batch itself
+    Fp = F // world if split else F
+    h_in = torch.empty((n_host, Fp, M, N), dtype=torch.float32).pin_memory()
+    h_in.copy_(d_pool[:n_host, rank * Fp:(rank + 1) * Fp].cpu() if split else d_pool[:n_host].cpu())
     h_out = torch.empty((2, F, D), dtype=torch.float32).pin_memory() if rank == 0 else None
     d_in = torch.empty((2, F, M, N), device="cuda")
+    d_part = torch.empty((2, Fp, M, N), device="cuda") if split else None
     d_asm = torch.empty((2, F, D), device="cuda") if rank == 0 else None
     s_in, s_run, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
     ev_in = [torch.cuda.Event() for _ in range(2)]
@@ -646,7 +677,11 @@ def e2e_sharded(torch, dist, nat, L, algo, d_pool, d_mics, n, D, F, M, N, rank, 
             with torch.cuda.stream(s_in):
                 if j >= 2:
                     s_in.wait_event(ev_run[sl])                  # the kernel that read this slot has finished
-                d_in[sl].copy_(h_in[i % n_host], non_blocking=True)
+                if split:
+                    d_part[sl].copy_(h_in[i % n_host], non_blocking=True)
+                    dist.all_gather_into_tensor(d_in[sl], d_part[sl])        # NVLink; stream-ordered behind the copy
+                else:
+                    d_in[sl].copy_(h_in[i % n_host], non_blocking=True)
                 ev_in[sl].record(s_in)
             with torch.cuda.stream(s_run):
                 s_run.wait_event(ev_in[sl])
@@ -657,7 +692,7 @@ def e2e_sharded(torch, dist, nat, L, algo, d_pool, d_mics, n, D, F, M, N, rank, 
                     if j >= 3:
                         s_run.wait_event(ev_out[pv])             # its previous D2H has left the assembly buffer
                     view = peer.ready(i - 1, s_run.cuda_stream)
-                    d_asm[pv].copy_(assemble_peer_layout(view, D))
+                    d_asm[pv].copy_(peer.assemble(view))
                     ev_asm[pv].record(s_run)
                     with torch.cuda.stream(s_out):
                         s_out.wait_event(ev_asm[pv])
@@ -668,7 +703,7 @@ def e2e_sharded(torch, dist, nat, L, algo, d_pool, d_mics, n, D, F, M, N, rank, 
             pv = i & 1
             with torch.cuda.stream(s_run):
                 view = peer.ready(i, s_run.cuda_stream)
-                d_asm[pv].copy_(assemble_peer_layout(view, D))
+                d_asm[pv].copy_(peer.assemble(view))
                 ev_asm[pv].record(s_run)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_asm[pv])
@@ -696,10 +731,12 @@ def e2e_sharded(torch, dist, nat, L, algo, d_pool, d_mics, n, D, F, M, N, rank, 
     dist.barrier()
     peer.close()
     return {"value": steps * F / float(t[0]), "unit": "maps/s", "steps": steps,
-            "h2d_bytes_per_step_per_rank": F * frame_bytes, "d2h_bytes_per_step_rank0": F * D * 4,
-            "host_maps_bit_exact_vs_one_gpu": ok,
-            "api": "host batch in (pinned, every rank) -> bf_mimo_dev_gather_sync (this rank's direction slice, peer "
-                   "stores) -> assembled maps out to the host on rank 0; copies inside the timed region"}
+            "h2d_bytes_per_step_per_rank": Fp * frame_bytes, "h2d_bytes_per_step": F * frame_bytes if split else world * F * frame_bytes,
+            "input_gather": "NCCL all-gather of the F frames over NVLink (%d frames per rank over PCIe)" % Fp if split else None,
+            "d2h_bytes_per_step_rank0": F * D * 4, "host_maps_bit_exact_vs_one_gpu": ok,
+            "api": "host batch in (pinned, F/world frames per rank) -> input all-gather -> bf_mimo_dev_gather_sync (this "
+                   "rank's direction slice, peer stores) -> assembled maps out to the host on rank 0; copies inside the "
+                   "timed region"}
 
 
 # ----------------------------------------------------------------------------------------
@@ -735,12 +772,16 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         setup = cpu_setup(args.workload, args.algo)
         cores = os.cpu_count() or 1
-        probe = cpu_run(args.workload, args.algo, 1, cores, setup)
-        maps_per_core = max(1, int(12.0 / max(probe["seconds"], 1e-3)))       # ~12 s of CPU work
+        libs = reference_builds(setup[1], setup[0])
+        probe = cpu_run(args.workload, args.algo, 1, cores, setup, libs[0])
+        maps_per_core = max(1, int(12.0 / len(libs) / max(probe["seconds"], 1e-3)))       # ~12 s of CPU work in all
         maps_per_core = min(maps_per_core, 200)
-        r = cpu_run(args.workload, args.algo, maps_per_core, cores, setup)
-        one = cpu_run(args.workload, args.algo, max(1, maps_per_core // 4), 1, setup)
+        runs = {lib: cpu_run(args.workload, args.algo, maps_per_core, cores, setup, lib) for lib in libs}
+        best = max(runs, key=lambda k: runs[k]["maps_per_s"])
+        r = runs[best]
+        one = cpu_run(args.workload, args.algo, max(1, maps_per_core // 4), 1, setup, best)
         cpu_base = {"value": r["maps_per_s"], "unit": "maps/s", "cores": cores, "kind": r["kind"],
+                    "builds_maps_per_s": {k: v["maps_per_s"] for k, v in runs.items()},
                     "sample": "%d whole %s maps (%d per core, one process per core), %.1f s"
                               % (r["maps"], args.workload.upper(), maps_per_core, r["seconds"]),
                     "one_core_maps_per_s": one["maps_per_s"],
@@ -793,14 +834,38 @@ def main():
     per, d_begin, d_count = shard_bounds(D, world, rank)
     pipe, peer = None, None
     gather_note = None
+    shard_note = None
     if world > 1 and args.gather == "p2p":
-        from lib.sharded import PeerGather
+        from lib.sharded import PeerGather, weighted_bounds
+        bounds = None
+        if os.environ.get("BF_SHARD_WEIGHTED", "1") != "0":
+            # the GPUs of a node do not all run at the same clock under load and a step is as fast as its slowest
+            # rank: time this rank's equal slice alone, share the times, and size the slices by measured speed
+            probe = torch.zeros((F, per), device="cuda")
+            ts = []
+            for i in range(4):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                nat.check(L.bf_mimo_dev_ex(algo, d_pool[i % pool].data_ptr(), probe.data_ptr(), F, d_mics.data_ptr(), n,
+                                           d_begin, max(d_count, 1), per, 1, d_begin, None))
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            tk = torch.zeros(world, device="cuda", dtype=torch.float64)
+            tk[rank] = float(np.mean(ts[1:]))
+            dist.all_reduce(tk, op=dist.ReduceOp.SUM)
+            bounds = weighted_bounds(D, [1.0 / float(x) for x in tk])
+            d_begin, d_count = bounds[rank]
+            shard_note = {"equal_slice_kernel_ms": [float(x) for x in tk], "directions_per_rank": [c for _, c in bounds]}
+            del probe
         try:
-            peer = PeerGather(D, F, rank, world, dist, depth=int(os.environ.get("BF_GATHER_DEPTH", "2")))   # kernel stores into every rank's buffer
+            peer = PeerGather(D, F, rank, world, dist, depth=int(os.environ.get("BF_GATHER_DEPTH", "2")),
+                              bounds=bounds)   # kernel stores into every rank's buffer
             d_maps = torch.zeros((F, D), device="cuda")
             fs, ds = D, 1
         except RuntimeError as e:               # raised on every rank together: fall back to the NCCL route
             peer, gather_note = None, str(e)
+            per, d_begin, d_count = shard_bounds(D, world, rank)
     if world > 1 and peer is None:
         from lib.sharded import GatherPipeline
         pipe = GatherPipeline(D, F, rank, world, torch.device("cuda"), dist)   # direction-major, gather in place
@@ -894,6 +959,12 @@ def main():
         torch.cuda.synchronize()
         kt.append(a.elapsed_time(b))
     k_ms = float(np.mean(kt))
+    per_rank_kernel_ms = None
+    if world > 1:                                    # every rank's slice kernel alone: which GPU sets the pace
+        tk = torch.zeros(world, device="cuda", dtype=torch.float64)
+        tk[rank] = k_ms
+        dist.all_reduce(tk, op=dist.ReduceOp.SUM)
+        per_rank_kernel_ms = [float(x) for x in tk]
     table_bytes = D * n * 4 * (2 if args.algo == "lerp" else 1)
     map_bytes = frame_bytes + table_bytes + D * 4                 # table every map
     launch_bytes = F * map_bytes * (d_count / D)
@@ -905,11 +976,40 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel": "das_mimo_kernel<%s>" % args.algo, "kernel_ms": k_ms,
-                "algorithmic_bytes_per_launch": launch_bytes,
+                "algorithmic_bytes_per_launch": launch_bytes, "per_rank_kernel_ms": per_rank_kernel_ms,
                 "accounting": "table counted once per map (SURVEY 8d primary); per launch = F maps",
                 "actual_bound": "fp32 issue (FADD2/FFMA2) -- dense maps are ~63 adds/byte, see DESIGN.md",
                 "fp32_lane_ops_per_s": adds / (k_ms * 1e-3),
                 "fp32_frac_of_148x128_lanes": (adds / (k_ms * 1e-3)) / fp32_peak if fp32_peak else None}
+
+    # ---- the opt-in tolerance mode beside the configured one (exact_sum = 2: shared-sum kernel) -----------
+    shared_sum = None
+    if world == 1 and args.exact_sum != 2 and not args.no_extras:
+        sig = d_pool[0]
+        ref_maps = torch.zeros((F, D), device="cuda")
+        nat.check(L.bf_mimo_dev_ex(algo, sig.data_ptr(), ref_maps.data_ptr(), F, d_mics.data_ptr(), n, 0, D, D, 1, 0, stream))
+        L.bf_set_kernel_options(0, 2)
+        tol_maps = torch.zeros((F, D), device="cuda")
+        ts = []
+        for i in range(6):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            nat.check(L.bf_mimo_dev_ex(algo, d_pool[i % pool].data_ptr(), tol_maps.data_ptr(), F, d_mics.data_ptr(), n,
+                                       0, D, D, 1, 0, stream))
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        nat.check(L.bf_mimo_dev_ex(algo, sig.data_ptr(), tol_maps.data_ptr(), F, d_mics.data_ptr(), n, 0, D, D, 1, 0, stream))
+        torch.cuda.synchronize()
+        L.bf_set_kernel_options(0, args.exact_sum)
+        rel = ((tol_maps.double() - ref_maps.double()).abs() / ref_maps.double().clamp_min(1e-300))
+        ms = float(np.mean(ts[1:]))
+        shared_sum = {"exact_sum": 2, "value": F / (ms * 1e-3), "unit": "maps/s", "kernel_ms": ms,
+                      "max_pixel_rel_err_vs_configured_mode": float(rel.max()), "mean_pixel_rel_err": float(rel.mean()),
+                      "tolerance": 1e-5,
+                      "note": "opt-in: microphones whose delay is uniform over a group of 8 directions are summed once per "
+                              "group (different rounding order); the headline stays on the configured exact_sum"}
+        del ref_maps, tol_maps
 
     # ---- e2e: the reference-facing call with host buffers -------------------------------------
     e2e, miso, mvdr, replay, heat, fir, latency = None, None, None, None, None, None, None
@@ -960,7 +1060,8 @@ def main():
         del h_pool, h_maps
         if world > 1 and peer is not None:
             try:
-                sh = e2e_sharded(torch, dist, nat, L, algo, d_pool, d_mics, n, D, F, M, N, rank, world, e2e_steps)
+                sh = e2e_sharded(torch, dist, nat, L, algo, d_pool, d_mics, n, D, F, M, N, rank, world, e2e_steps,
+                                 bounds=peer.bounds)
             except Exception as ex:  # noqa: BLE001  (every rank reaches the collectives inside or none does)
                 sh = {"error": str(ex)}
             e2e["partition"] = "replicas: each rank replays its own frames (recordings shard with no collective)"
@@ -1049,9 +1150,9 @@ def main():
                            world, (", all-gather fused into the kernel: epilogue stores go to every rank's buffer over NVLink peer memory"
                             if peer else ", one in-place NCCL all-gather per step on a second stream") if world > 1 else ""),
                        "exact_sum": args.exact_sum},
-            "sum_step_ms": dev_ms, "wall_s": t_wall, "gather_note": gather_note, "gpu_launches": launches, "clocks": clocks,
+            "sum_step_ms": dev_ms, "wall_s": t_wall, "gather_note": gather_note, "shard_weights": shard_note, "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "miso": miso, "mvdr": mvdr, "replay": replay, "heatmap": heat, "fir": fir,
-            "latency": latency,
+            "latency": latency, "shared_sum_mode": shared_sum,
             # last on purpose: the tail of the line is what a truncated log keeps
             "e2e_sharded_maps_per_s": (e2e or {}).get("sharded", {}).get("value") if isinstance((e2e or {}).get("sharded"), dict) else None,
             "gather_check": gather_check,

@@ -30,18 +30,35 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+def host_has_avx512():
+    """True when this host can run the x86-64-v4 build (libref_v4.so)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    fl = set(line.split(":", 1)[1].split())
+                    return {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= fl
+    except OSError:
+        pass
+    return False
+
+
+def v4_available(cfg):
+    return os.path.exists(os.path.join(ROOT, cfg, "libref_v4.so")) and host_has_avx512()
+
+
 class RefC:
     """ctypes view of one oracle/_ref/<cfg>/libref.so (process-global tables,
-    exactly like the reference)."""
+    exactly like the reference).  lib="libref_v4.so" selects the AVX-512 build."""
 
-    def __init__(self, cfg):
+    def __init__(self, cfg, lib="libref.so"):
         self.cfg = cfg
         self.g = general(cfg)
         self.N = self.g["N_SAMPLES"]
         self.M = self.g["N_MICROPHONES"]
         self.D = self.g["MAX_RES_X"] * self.g["MAX_RES_Y"]
         self.T = self.g["N_TAPS"]
-        self.L = ctypes.CDLL(os.path.join(ROOT, cfg, "libref.so"))
+        self.L = ctypes.CDLL(os.path.join(ROOT, cfg, lib))
         self._keep = []
 
     def _sig(self, s):

@@ -77,3 +77,17 @@ def test_ingest_restatement_vs_the_real_receiver(case, n_arrays):
     rows = (np.arange(n_ch) // 8) % 8
     assert bits_equal(fixed[:n_ch][rows % 2 == 0], want[:n_ch][rows % 2 == 0])
     assert not bits_equal(fixed[:n_ch][rows % 2 == 1], want[:n_ch][rows % 2 == 1])
+
+
+@pytest.mark.skipif(not ref.v4_available("c1"), reason="no AVX-512 on this host or libref_v4.so not built")
+def test_avx512_build_of_the_reference_is_bitwise_the_portable_one():
+    """bench.py's reference arm may time libref_v4.so (-march=x86-64-v4, what the reference's -march=native gives
+    on an AVX-512 host) beside libref.so (-mavx2 -mfma): same source, and the outputs must be the same bits."""
+    a, b = ref.RefC("c1"), ref.RefC("c1", "libref_v4.so")
+    rng = np.random.default_rng(3)
+    sig = rng.standard_normal((a.M, a.N)).astype(np.float32)
+    mics = np.arange(a.M, dtype=np.int32)
+    whole = rng.integers(0, 48, (a.D, a.M)).astype(np.int32)
+    d32 = (rng.random((a.D, a.M)) * 47.5).astype(np.float32)
+    assert bits_equal(a.mimo_pad(sig, mics, whole), b.mimo_pad(sig, mics, whole))
+    assert bits_equal(a.mimo_lerp(sig, mics, d32), b.mimo_lerp(sig, mics, d32))

@@ -96,3 +96,19 @@ def test_peer_gather_layout_model():
                 for d in range(d_begin, d_begin + d_count):
                     flat[rank * F * per + f * per + (d - d_begin)] = maps[f, d]      # what the epilogue stores
         assert np.array_equal(assemble_peer_layout(buf, D), maps)
+
+
+def test_weighted_bounds_tile_the_grid():
+    """Slices sized by measured per-GPU speed (lib.sharded.weighted_bounds): contiguous, in rank order, whole
+    8-direction groups except at the end of the grid, proportional to the weights, equal weights -> equal slices."""
+    from lib.sharded import weighted_bounds
+    for D, w in ((32400, [1 / 1.244, 1 / 1.276, 1 / 1.265, 1 / 1.291, 1 / 1.265, 1 / 1.279, 1 / 1.251, 1 / 1.280]),
+                 (400, [1, 1, 1]), (91, [3, 1]), (8, [1, 1, 1, 1])):
+        b = weighted_bounds(D, w)
+        assert len(b) == len(w) and b[0][0] == 0 and sum(c for _, c in b) == D
+        for r in range(len(b) - 1):
+            assert b[r][0] + b[r][1] == b[r + 1][0] and b[r][1] >= 0 and b[r + 1][0] % 8 == 0
+        share = np.array([c for _, c in b]) / D
+        assert np.all(np.abs(share - np.array(w) / np.sum(w)) <= 8 / D + 1e-9)
+    eq = weighted_bounds(32400, [1.0] * 8)
+    assert max(c for _, c in eq) - min(c for _, c in eq) <= 8

@@ -428,16 +428,27 @@ int miso_run(int algo, const float *d_sig, float *d_out, int blocks, const int *
     // Measured on B200 (tools/miso_sweep.py, C2): contiguous microphone ids (one 32 KiB copy per
     // stage) -> 2 CTAs/SM x 2 stages: 6.9 TB/s pad, 6.8 TB/s lerp; scattered ids (1 KiB copies)
     // -> 3 CTAs/SM x 2 stages: 6.8 / 5.9 TB/s.
+    // whether the microphone ids are mostly consecutive decides the launch shape; the ids are read back once per
+    // (pointer, n).  While the stream is being captured into a CUDA graph a blocking copy is not allowed: an
+    // unknown array is then treated as scattered (3 CTAs per SM, per-row copies: correct for any ids).
     static const int *s_key_ptr = nullptr; static int s_key_n = -1; static bool s_contig = false;
+    bool contig = s_contig;
     if (s_key_ptr != d_mics || s_key_n != n) {
-        std::vector<int> h(n);
-        BF_CUDA(cudaMemcpy(h.data(), d_mics, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
-        int breaks = 0;
-        for (int m = 1; m < n; m++) breaks += (h[m] != h[m - 1] + 1);
-        s_contig = breaks * 8 <= n;            // mostly runs of >= 8 rows
-        s_key_ptr = d_mics; s_key_n = n;
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+        if (cap == cudaStreamCaptureStatusNone) {
+            std::vector<int> h(n);
+            BF_CUDA(cudaMemcpyAsync(h.data(), d_mics, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+            BF_CUDA(cudaStreamSynchronize(st));
+            int breaks = 0;
+            for (int m = 1; m < n; m++) breaks += (h[m] != h[m - 1] + 1);
+            s_contig = contig = breaks * 8 <= n;            // mostly runs of >= 8 rows
+            s_key_ptr = d_mics; s_key_n = n;
+        } else {
+            contig = false;
+        }
     }
-    int ctas = s_contig ? 2 : 3;
+    int ctas = contig ? 2 : 3;
     while (ctas > 1 && (N + 32) * ctas > 2048) ctas--;
     if (const char *e = getenv("BF_MISO_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 4 && (N + 32) * v <= 2048) ctas = v; }
     const size_t budget = (size_t)(227 * 1024) / ctas - 1024 - 256 - tab_bytes - 1024;

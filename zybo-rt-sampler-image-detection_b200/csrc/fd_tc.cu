@@ -15,18 +15,18 @@
 // so a thread (= TMEM lane = direction) ends up owning all 512 Y values of its direction and
 // q(d) is a private sum of squares: no cross-thread reduction.
 //
-// Precision: kind::tf32 with an error-compensated split x = hi + lo (hi = x with the low 13
-// mantissa bits cleared, lo = x - hi exactly): three passes A_hi*B_hi + A_hi*B_lo + A_lo*B_hi
-// (~2^-21 per product), fp32 accumulation.  "Issued" tensor flops are therefore 3x the useful
-// 8*M^2 per (bin, direction); the triangular structure of L^-1 lets N-tile 0 skip the second
-// half of K (-25 %).
+// Three generations live here (BF_MVDR_TC selects; 3 is the default):
+//   1  mvdr_tc_steer_kernel   one CTA per (bin, 128 directions), generate -> copy -> MMA serially, kind::tf32
+//   2  mvdr_tc_steer_kernel2  persistent, warp-specialised, double-buffered, kind::tf32 with a 3-pass tf32 split
+//                             (x = hi + lo, hi = x with the low 13 mantissa bits cleared)  -- round 1
+//   3  mvdr_tc_steer_kernel3  the same roles with kind::f16 and a two-term fp16 split, a converged MMA warp
+//                             (descriptors in uniform registers) and fixed-point phases         -- round 2, shipped
+// "Issued" tensor flops are 3x the useful 8*M^2 per (bin, direction); the triangular structure of L^-1 lets
+// N-tile 0 skip the second half of K (-25 %): issued = 2.25 x useful.
 //
-// Shared-memory operand layout: K-major, 128-byte rows (32 tf32 = 16 microphones per k-chunk),
-// SWIZZLE_128B (16-byte chunk index XOR (row & 7)), 8-row groups of 1024 bytes
-// (stride_byte_offset = 1024); one k-chunk = 4 MMA k-steps of 8 (descriptor start + 32 B).
-//
-// First correct version: single-buffered (generate/copy, then MMA, then next chunk); the
-// pipelined, multicast version is the round-2 item.
+// Shared-memory operand layout: K-major, 128-byte rows (32 tf32 = 16 microphones, or 64 halves = 32 microphones,
+// per k-chunk), SWIZZLE_128B (16-byte chunk index XOR (row & 7)), 8-row groups of 1024 bytes
+// (stride_byte_offset = 1024); one k-chunk = 4 MMA k-steps of 32 bytes (descriptor start + 32 B).
 #include <math.h>
 #include <cuda_fp16.h>
 

@@ -22,6 +22,23 @@ def shard_bounds(n_directions, world, rank):
     return per, d_begin, d_count
 
 
+def weighted_bounds(n_directions, weights, multiple=8):
+    """Direction slices proportional to `weights` (one per rank, e.g. 1 / measured kernel time of that GPU), in
+    multiples of `multiple` directions (the kernel's group size) except the last: -> list of (d_begin, d_count).
+    On a node whose GPUs do not run at the same clock the step is as fast as its slowest rank; giving that rank
+    fewer directions evens the ranks out."""
+    w = np.asarray(weights, np.float64)
+    w = w / w.sum()
+    edges = np.round(np.cumsum(w) * n_directions / multiple).astype(np.int64) * multiple
+    edges[-1] = n_directions
+    edges = np.minimum(np.maximum.accumulate(edges), n_directions)
+    out, begin = [], 0
+    for e in edges:
+        out.append((int(begin), int(e - begin)))
+        begin = int(e)
+    return out
+
+
 class ShardedMaps:
     """maps = ShardedMaps(D, frames, rank, world, device); maps.compute(fn); maps.gather()
 
@@ -122,7 +139,9 @@ class PeerGather:
     depth >= consume_lag + 2).  maps(i) is the assembled [F][D] tensor of step i.
     """
 
-    def __init__(self, n_directions, frames, rank, world, dist, depth=2, consume_lag=0):
+    def __init__(self, n_directions, frames, rank, world, dist, depth=2, consume_lag=0, bounds=None):
+        """bounds: optional list of (d_begin, d_count) per rank (weighted_bounds) instead of equal slices; the
+        gather buffers are sized for the largest slice and maps() drops the padding."""
         import ctypes
         if depth < consume_lag + 2:
             raise ValueError("PeerGather: depth must be at least consume_lag + 2")
@@ -132,6 +151,16 @@ class PeerGather:
         self.torch, self.nat, self.L = torch, _native, _native.lib()
         self.D, self.F, self.rank, self.world, self.depth = n_directions, frames, rank, world, depth
         self.per, self.d_begin, self.d_count = shard_bounds(n_directions, world, rank)
+        self.bounds = None
+        if bounds is not None:
+            bounds = [(int(b), int(c)) for b, c in bounds]
+            if len(bounds) != world or bounds[0][0] != 0 or any(c < 0 for _, c in bounds) or \
+                    any(bounds[r][0] + bounds[r][1] != (bounds[r + 1][0] if r + 1 < world else n_directions)
+                        for r in range(world)):
+                raise ValueError("PeerGather: bounds must tile [0, D) in rank order")
+            self.bounds = bounds
+            self.per = max(c for _, c in bounds)
+            self.d_begin, self.d_count = bounds[rank]
         L = self.L
         vp = ctypes.c_void_p
         n_buf = world * frames * self.per
@@ -245,9 +274,15 @@ class PeerGather:
                                              self.timed_out.data_ptr(), st))
         return self.views[i % self.depth]
 
+    def assemble(self, view):
+        """[world][F][per] gather view -> [F][D] maps (a copy; drops the padding of unequal slices)."""
+        if self.bounds is not None:
+            return self.torch.cat([view[r, :, :c] for r, (_, c) in enumerate(self.bounds)], dim=1)
+        return assemble_peer_layout(view, self.D)
+
     def maps(self, i):
         """[F][D] tensor of step i (a copy: the gather layout is [rank][F][per]); waits for the step."""
-        return assemble_peer_layout(self.ready(i), self.D)
+        return self.assemble(self.ready(i))
 
     def check(self):
         if int(self.timed_out.item()):

@@ -271,8 +271,8 @@ def mvdr_c4(nat, L, torch, stream, bins=512, dirs=32768, K=64):
     """BASELINE config C4: frequency-domain MVDR, 256 mics, 1024-point FFT, bins 1..512, K = 64
     snapshots, 256 x 128 directions.  Useful flops of the steering contraction: 8*D*M^2*F
     (SURVEY.md 8d).  Tensor roofline = useful flops / steering-kernel time against the measured
-    dense bf16 peak; the kernel issues 2.25x that as kind::f16 MMAs (3-pass two-term fp16 split, -25 %
-    triangular skip)."""
+    dense bf16 peak; the kernel issues 1.875x that as kind::f16 MMAs (3-pass two-term fp16 split, 20 of 32
+    (k-chunk, row-quarter) items thanks to the triangular L^-1)."""
     import realtime_scripts.calc_r_prime as rp
     import realtime_scripts.config as cfg
     M, N, F = 256, 1024, bins
@@ -314,9 +314,9 @@ def mvdr_c4(nat, L, torch, stream, bins=512, dirs=32768, K=64):
             "stage_ms": dict(zip(["fft_f64", "covariance_f64", "cholesky_f64", "tri_inverse_f64", "steering_tcgen05"],
                                  [float(x) for x in stage])),
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                         "kernel": "mvdr_tc_steer_kernel3 (tcgen05 kind::f16, 3-pass two-term fp16 split)",
+                         "kernel": "mvdr_tc_steer_kernel3<QUARTER> (tcgen05 kind::f16, 3-pass two-term fp16 split, N = 128)",
                          "kernel_ms": float(stage[4]), "useful_flops_per_launch": useful,
-                         "issued_over_useful": 2.25, "traffic": None,
+                         "issued_over_useful": 1.875, "traffic": None,
                          "tensor_pipe_active_pct_ncu": _traffic("mvdr_tc_steer_tensor_pipe_active_pct"),
                          "peak_source": "measured dense bf16 burst (MEASURED_PEAKS.json)"}}
 

@@ -250,6 +250,22 @@ typedef struct bf_datagram_header {
     /* int32_t stream[N_MICROPHONES] follows */
 } bf_datagram_header;
 
+/* ---- the reference's shared-memory records with run-time sizes ---------------
+ * api.h:26-30   typedef struct { int can_read; float out[N_SAMPLES]; } paData;
+ * api.h:32-38   typedef struct { int steer_offset; float signals[BUFFER_LENGTH];
+ *                                int adaptive_array[N_MICROPHONES]; int n; } Miso;
+ * receiver.h:31-36  typedef struct { int index; float data[BUFFER_LENGTH * 4]; int counter; } ring_buffer;
+ * (receiver.h:51-59 `msg` is bf_datagram_header + the payload.)  The reference fixes the array sizes with macros;
+ * here they follow from the configured sizes: bf_layout_* return the record size and the byte offset of every
+ * member in declaration order.  bf_miso_record_listen runs one iteration of the audio child's loop
+ * (api.c:505-529) on a Miso record in host / SysV shared memory: the steered beam of miso->signals, and -- when
+ * padata_record is not NULL -- the post-scale out / n * MIC_GAIN into pa->out with pa->can_read = 1. */
+typedef struct bf_record_layout { size_t size; size_t off[4]; } bf_record_layout;
+bf_record_layout bf_layout_miso(int n_microphones, int n_samples);        /* steer_offset, signals, adaptive_array, n */
+bf_record_layout bf_layout_padata(int n_samples);                         /* can_read, out */
+bf_record_layout bf_layout_ring_buffer(int n_microphones, int n_samples); /* index, data, counter */
+int bf_miso_record_listen(const void *miso_record, void *padata_record);
+
 /* ---- wire-format ingest (receiver.c:94-151), SURVEY 8f "next" #1 -------------------------
  * d_stream  device int32 [frames][n_samples][n_microphones]: the `stream` payload of
  *           n_samples consecutive datagrams (receiver.h:51-59), header stripped

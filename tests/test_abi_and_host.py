@@ -156,3 +156,26 @@ def test_synthetic_inputs_are_deterministic():
     sig = synthetic.point_sources(g["delays"].reshape(-1, 64), g["mic_ids"], 64, 256, 48828.0,
                                   synthetic.C1["sources"], synthetic.C1["noise"], synthetic.C1["seed"])
     assert np.allclose(sig, g["signals"], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("cfg,M,N", [("default", 256, 256), ("c1", 64, 256)])
+def test_shared_memory_record_layouts_match_the_reference_headers(cfg, M, N):
+    """bf_layout_{miso,padata,ring_buffer} reproduce sizeof / offsetof of the reference's own
+    structs (api.h:26-38, receiver.h:31-36) as compiled from its headers for this configuration
+    (oracle/build_ref.py:build_record_layouts -> oracle/_ref/<cfg>/record_layouts.json), and bf_datagram_header
+    is the head of receiver.h:51-59 `msg`."""
+    import json
+    path = os.path.join(ROOT, "oracle", "_ref", cfg, "record_layouts.json")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built")
+    ref = json.load(open(path))
+    from lib import _native
+    L = _native.lib()
+    lm = L.bf_layout_miso(M, N)
+    assert [lm.size, *lm.off] == ref["Miso"]
+    lp = L.bf_layout_padata(N)
+    assert [lp.size, lp.off[0], lp.off[1]] == ref["paData"]
+    lr = L.bf_layout_ring_buffer(M, N)
+    assert [lr.size, lr.off[0], lr.off[1], lr.off[2]] == ref["ring_buffer"]
+    import struct
+    assert ref["msg"] == [8 + 4 * M, 0, 2, 3, 4, 8] and struct.calcsize("<Hbbi") == 8      # bf_datagram_header

@@ -230,6 +230,36 @@ def test_miso_beam_listen_and_steering():
         beamformer.disconnect()
 
 
+def test_miso_record_listen_on_the_reference_shm_layout():
+    """one iteration of the reference's audio child (api.c:505-529) on a `Miso` record laid out
+    as api.h:32-38 declares it (what load_pa() / steer() write into the SysV segment) and a `paData` record
+    (api.h:26-30): beam of miso->signals at miso->steer_offset, post-scaled into pa->out, pa->can_read = 1."""
+    import ctypes
+    config, nat, L = _setup("c1")
+    from oracle import cpu
+    from lib import directions
+    g = gold("c1")
+    M, N = 64, 256
+    whole, _ = directions.whole_and_f32()
+    L.load_coefficients_pad(nat.ptr(whole), whole.size)
+    nat.check()
+    mics = nat.i32(g["mic_ids"])
+    n = len(mics)
+    off = (6 * 20 + 14) * n
+    lm, lp = L.bf_layout_miso(M, N), L.bf_layout_padata(N)
+    rec = np.zeros(lm.size, np.uint8)
+    rec[lm.off[0]:lm.off[0] + 4] = np.array([off], np.int32).view(np.uint8)
+    rec[lm.off[1]:lm.off[1] + M * N * 4] = np.ascontiguousarray(g["signals"], np.float32).view(np.uint8).ravel()
+    rec[lm.off[2]:lm.off[2] + n * 4] = mics.view(np.uint8)
+    rec[lm.off[3]:lm.off[3] + 4] = np.array([n], np.int32).view(np.uint8)
+    pa = np.zeros(lp.size, np.uint8)
+    nat.check(L.bf_miso_record_listen(nat.ptr(rec), nat.ptr(pa)))
+    assert pa[:4].view(np.int32)[0] == 1
+    got = pa[lp.off[1]:].view(np.float32)
+    ref = cpu.miso_scale(cpu.miso_pad(g["signals"], mics, whole, off), n, 128.0)
+    assert bits_equal(got, ref)
+
+
 @pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("algo_name", ["pad", "lerp"])
 def test_host_batch_replay_equals_per_buffer_calls(algo_name, pinned):

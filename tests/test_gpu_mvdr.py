@@ -66,9 +66,10 @@ def _oracle(snaps, g, loading):
     return R, P, Pdas
 
 
-@pytest.mark.parametrize("tensor_cores", [0, 1, 2, 3])
+@pytest.mark.parametrize("tensor_cores", [0, 1, 2, 3, 4])
 def test_mvdr_against_float64_oracle_and_das_anchor(tensor_cores, monkeypatch):
-    """tensor_cores=3 (default): warp-specialised tcgen05 steering contraction, kind::f16 with a two-term
+    """tensor_cores=4 (default): as 3 with N = 128 MMAs and quarter-granular triangular skipping;
+    tensor_cores=3: warp-specialised tcgen05 steering contraction, kind::f16 with a two-term
     fp16 split; 2: the same with kind::tf32 (3-pass split tf32); 1: its single-buffered first version;
     0: CUDA-core fp32."""
     monkeypatch.setenv("BF_MVDR_TC", str(tensor_cores))

@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--dirs", type=int, default=32768)
     ap.add_argument("--snapshots", type=int, default=64)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--tc", type=int, default=3)
+    ap.add_argument("--tc", type=int, default=4)
     args = ap.parse_args()
     os.environ["BF_MVDR_TC"] = str(args.tc)
     import torch

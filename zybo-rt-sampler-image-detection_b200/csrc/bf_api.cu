@@ -877,4 +877,61 @@ void miso_steer_listen(float *out, int *adaptive_array, int n, int steer_offset)
     if (sourced(&sig) == BF_OK) host_miso(BF_ALGO_PAD, sig, out, adaptive_array, n, steer_offset, 0);
 }
 
+// ---- the reference's shared-memory records, with run-time sizes (api.h:26-38, receiver.h:31-36) ----
+// All members are 4-byte types in declaration order, so the layouts are plain running sums.
+bf_record_layout bf_layout_miso(int n_microphones, int n_samples)
+{
+    bf_record_layout l{};
+    l.off[0] = 0;                                                   // int steer_offset
+    l.off[1] = 4;                                                   // float signals[BUFFER_LENGTH]
+    l.off[2] = l.off[1] + (size_t)n_microphones * n_samples * 4;    // int adaptive_array[N_MICROPHONES]
+    l.off[3] = l.off[2] + (size_t)n_microphones * 4;                // int n
+    l.size = l.off[3] + 4;
+    return l;
+}
+bf_record_layout bf_layout_padata(int n_samples)
+{
+    bf_record_layout l{};
+    l.off[0] = 0;                                                   // int can_read
+    l.off[1] = 4;                                                   // float out[N_SAMPLES]
+    l.size = 4 + (size_t)n_samples * 4;
+    return l;
+}
+bf_record_layout bf_layout_ring_buffer(int n_microphones, int n_samples)
+{
+    bf_record_layout l{};
+    l.off[0] = 0;                                                   // int index
+    l.off[1] = 4;                                                   // float data[BUFFER_LENGTH * 4]
+    l.off[2] = 4 + (size_t)n_microphones * n_samples * 4 * 4;       // int counter
+    l.size = l.off[2] + 4;
+    return l;
+}
+
+// One iteration of the reference's audio child (api.c:505-529, miso_loop) on a `Miso` record in host (shared)
+// memory: miso_pad(miso->signals, out, miso->adaptive_array, miso->n, miso->steer_offset), then, when `pa` is
+// not NULL, the post-scale out[i] / n * MIC_GAIN into pa->out and pa->can_read = 1.
+int bf_miso_record_listen(const void *miso_record, void *padata_record)
+{
+    State &S = state();
+    const bf_record_layout lm = bf_layout_miso(S.cfg.n_microphones, S.cfg.n_samples);
+    if (!miso_record) { set_error(BF_ERR_ARG, "bf_miso_record_listen: null record"); return BF_ERR_ARG; }
+    const char *m = (const char *)miso_record;
+    const int steer_offset = *(const int *)(m + lm.off[0]);
+    const float *signals = (const float *)(m + lm.off[1]);
+    const int *adaptive = (const int *)(m + lm.off[2]);
+    const int n = *(const int *)(m + lm.off[3]);
+    std::vector<float> out((size_t)S.cfg.n_samples);
+    int rc = host_miso(BF_ALGO_PAD, signals, out.data(), adaptive, n, steer_offset, 0);
+    if (rc) return rc;
+    if (padata_record) {
+        const bf_record_layout lp = bf_layout_padata(S.cfg.n_samples);
+        char *pa = (char *)padata_record;
+        float *dst = (float *)(pa + lp.off[1]);
+        const float fn = (float)n, gain = S.cfg.mic_gain;
+        for (int i = 0; i < S.cfg.n_samples; i++) dst[i] = out[i] / fn * gain;          // api.c:519-523
+        *(int *)(pa + lp.off[0]) = 1;
+    }
+    return BF_OK;
+}
+
 }  // extern "C"

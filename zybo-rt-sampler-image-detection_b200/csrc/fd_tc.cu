@@ -15,14 +15,16 @@
 // so a thread (= TMEM lane = direction) ends up owning all 512 Y values of its direction and
 // q(d) is a private sum of squares: no cross-thread reduction.
 //
-// Three generations live here (BF_MVDR_TC selects; 3 is the default):
+// Generations living here (BF_MVDR_TC selects; 4 is the default):
 //   1  mvdr_tc_steer_kernel   one CTA per (bin, 128 directions), generate -> copy -> MMA serially, kind::tf32
 //   2  mvdr_tc_steer_kernel2  persistent, warp-specialised, double-buffered, kind::tf32 with a 3-pass tf32 split
 //                             (x = hi + lo, hi = x with the low 13 mantissa bits cleared)  -- round 1
 //   3  mvdr_tc_steer_kernel3  the same roles with kind::f16 and a two-term fp16 split, a converged MMA warp
-//                             (descriptors in uniform registers) and fixed-point phases         -- round 2, shipped
+//                             (descriptors in uniform registers) and fixed-point phases         -- round 2
+//   4  mvdr_tc_steer_kernel3<QUARTER>  the same with N = 128 MMAs and quarter-granular triangular skipping
+//                             (20 instead of 24 half-tile equivalents per unit)                 -- round 2, shipped
 // "Issued" tensor flops are 3x the useful 8*M^2 per (bin, direction); the triangular structure of L^-1 lets
-// N-tile 0 skip the second half of K (-25 %): issued = 2.25 x useful.
+// N-tile 0 skip the second half of K (-25 %): issued = 2.25 x useful (generation 4: 20 / 32 quarters: 1.875 x).
 //
 // Shared-memory operand layout: K-major, 128-byte rows (32 tf32 = 16 microphones, or 64 halves = 32 microphones,
 // per k-chunk), SWIZZLE_128B (16-byte chunk index XOR (row & 7)), 8-row groups of 1024 bytes
@@ -456,6 +458,12 @@ static constexpr int kV3Chunks = 2 * kTcMics / kV3Kc;            // 8
 static constexpr int kV3GenWarps = 16;
 static constexpr int kV3Threads = (6 + kV3GenWarps) * 32;        // 704
 __device__ __forceinline__ int v3_chunk(int i) { return (i & 1) ? kV3Chunks / 2 + (i >> 1) : (i >> 1); }
+// QUARTER variant (BF_MVDR_TC=4): N = 128 MMAs, the 512 rows of L^-1 in four quarters of 64 microphones; k-chunk c
+// (microphones 32c .. 32c+31) only feeds quarters t >= c / 2 (L^-1 is lower triangular): 4,4,3,3,2,2,1,1 = 20 of 32
+// (chunk, quarter) items instead of the 24 half-tile equivalents of the N = 256 version (-17 % MMA work).  Chunks are
+// visited 0,7,1,6,2,5,3,4 so that every pair of chunks carries 5 items.
+__device__ __forceinline__ int v3q_chunk(int i) { return (i & 1) ? kV3Chunks - 1 - (i >> 1) : (i >> 1); }
+template <bool QUARTER> __device__ __forceinline__ int v3_order(int i) { return QUARTER ? v3q_chunk(i) : v3_chunk(i); }
 
 // per bin: exponent e with max_ij(|Lr|,|Li|) * 2^e in [2^7, 2^8); binscale = 2^-(e+8) undoes it and the 2^8 of the
 // phasors.  One scale per bin (not per row) keeps the epilogue free of per-column loads; rows whose entries
@@ -548,22 +556,32 @@ __global__ void mvdr_tc_phifix_kernel(const double *__restrict__ u, int D, doubl
 }
 
 // (cos, -sin) of 2 pi x / 2^32 for a 32-bit fixed-point phase x (turns): the phasor exp(-j 2 pi x / 2^32).
-// Quadrant by integer arithmetic, then fp32 polynomials on [-pi/4, pi/4] (truncation error < 2e-9).
+// Quadrant by integer arithmetic, then on [-pi/4, pi/4] either fp32 polynomials (truncation error < 2e-9,
+// FAST = false) or the SFU's MUFU.SIN / MUFU.COS (FAST = true: 2 special-function ops instead of 11 FMAs; on this
+// reduced range their absolute error is ~2^-21.4, an order of magnitude below the map tolerance -- measured in
+// tests/test_gpu_c4_size.py).
+template <bool FAST>
 __device__ __forceinline__ void phasor_fix(uint32_t x, float &cs, float &sn)
 {
     const uint32_t q = (x + 0x20000000u) >> 30;                      // nearest quarter turn, 0..3 (4 wraps to 0)
     const int32_t r = (int32_t)(x - (q << 30));                      // [-2^29, 2^29)
     const float z = (float)r * 1.4629180792671596e-09f;              // 2 pi / 2^32
-    const float z2 = z * z;
-    float s = fmaf(z2, 2.7557319e-06f, -1.9841270e-04f);             // z - z^3/3! + z^5/5! - z^7/7! + z^9/9!
-    s = fmaf(s, z2, 8.3333333e-03f);
-    s = fmaf(s, z2, -1.6666667e-01f);
-    s = fmaf(s * z2, z, z);
-    float c = fmaf(z2, -2.7557319e-07f, 2.4801587e-05f);             // 1 - z^2/2! + z^4/4! - z^6/6! + z^8/8! - z^10/10!
-    c = fmaf(c, z2, -1.3888889e-03f);
-    c = fmaf(c, z2, 4.1666667e-02f);
-    c = fmaf(c, z2, -0.5f);
-    c = fmaf(c, z2, 1.0f);
+    float s, c;
+    if (FAST) {
+        s = __sinf(z);
+        c = __cosf(z);
+    } else {
+        const float z2 = z * z;
+        s = fmaf(z2, 2.7557319e-06f, -1.9841270e-04f);               // z - z^3/3! + z^5/5! - z^7/7! + z^9/9!
+        s = fmaf(s, z2, 8.3333333e-03f);
+        s = fmaf(s, z2, -1.6666667e-01f);
+        s = fmaf(s * z2, z, z);
+        c = fmaf(z2, -2.7557319e-07f, 2.4801587e-05f);               // 1 - z^2/2! + z^4/4! - z^6/6! + z^8/8! - z^10/10!
+        c = fmaf(c, z2, -1.3888889e-03f);
+        c = fmaf(c, z2, 4.1666667e-02f);
+        c = fmaf(c, z2, -0.5f);
+        c = fmaf(c, z2, 1.0f);
+    }
     // angle = q * pi/2 + z:  cos, sin = (c, s), (-s, c), (-c, -s), (s, -c)
     const float a = (q & 1u) ? s : c, b = (q & 1u) ? c : s;
     const float co = ((q + 1u) & 2u) ? -a : a;
@@ -596,20 +614,24 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t *bar)
         ::"r"(bfptx::smem_u32(bar)) : "memory");
 }
 
+template <bool QUARTER>
 __global__ void __launch_bounds__(kV3Threads, 1) mvdr_tc_steer_kernel3(const unsigned char *__restrict__ image,
                                                                        const uint32_t *__restrict__ phifix,
                                                                        const float *__restrict__ colscale, int F, int lo,
                                                                        int D, int tiles, float *__restrict__ qout, int dbg)
 {
-    // dbg (BF_MVDR_DBG, timing experiments only -- results are wrong): bit 0 generators skip the sincos,
-    // bit 1 the producer skips the B copies
+    // dbg (BF_MVDR_DBG): timing experiments, results are wrong -- bit 0 generators skip the sincos, bit 1 the
+    // producer skips the B copies; bit 2 (results valid): polynomial phasors instead of MUFU.SIN / MUFU.COS
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sA = smem;                                  // 2 x 32 KiB (hi + lo planes of 128 rows)
     unsigned char *sB = smem + 2 * kV2BufA;                    // 2 x 64 KiB (hi + lo planes of 256 rows)
+    constexpr int NB = QUARTER ? 4 : 2;                       // B ring slots (32 KiB quarters or 64 KiB halves)
+    constexpr uint32_t kSlotB = QUARTER ? (uint32_t)kV2SlotB / 2 : (uint32_t)kV2SlotB;
+    constexpr uint32_t kRowsB = QUARTER ? 128u : 256u;        // rows per slot = MMA N
     uint64_t *bars = (uint64_t *)(sB + 2 * kV2SlotB);
-    uint64_t *a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 6;
-    uint64_t *t0_done = bars + 8, *acc_done = bars + 9, *acc_free = bars + 10;
-    uint32_t *tmem_slot = (uint32_t *)(bars + 11);
+    uint64_t *a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 8;
+    uint64_t *t0_done = bars + 12, *acc_done = bars + 13, *acc_free = bars + 14;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 15);
 
     const int t = threadIdx.x, lane = t & 31;
     // warp index as a warp-uniform value: the role dispatch below is then a uniform branch and the MMA warp's
@@ -621,6 +643,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) mvdr_tc_steer_kernel3(const uns
         for (int i = 0; i < 2; i++) {
             bfptx::mbar_init(&a_full[i], kV3GenWarps);
             bfptx::mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < NB; i++) {
             bfptx::mbar_init(&b_full[i], 1);
             bfptx::mbar_init(&b_empty[i], 1);
         }
@@ -647,16 +671,17 @@ __global__ void __launch_bounds__(kV3Threads, 1) mvdr_tc_steer_kernel3(const uns
                 const int f = unit / tiles;
                 const unsigned char *img = image + (size_t)f * kV3Chunks * 2 * kTcPlaneB;
                 for (int ci = 0; ci < kV3Chunks; ci++) {
-                    const int chunk = v3_chunk(ci);
-                    for (int nt = (chunk < kV3Chunks / 2 ? 0 : 1); nt < 2; nt++, k++) {
-                        const uint32_t slot = k & 1, ph = (k >> 1) & 1;
+                    const int chunk = v3_order<QUARTER>(ci);
+                    const int nt0 = QUARTER ? (chunk >> 1) : (chunk < kV3Chunks / 2 ? 0 : 1);
+                    for (int nt = nt0; nt < (QUARTER ? 4 : 2); nt++, k++) {
+                        const uint32_t slot = k % NB, ph = (k / NB) & 1;
                         bfptx::mbar_wait(&b_empty[slot], ph ^ 1);
-                        unsigned char *dst = sB + slot * kV2SlotB;
-                        const unsigned char *src = img + (size_t)chunk * 2 * kTcPlaneB + (size_t)nt * 256 * 128;
+                        unsigned char *dst = sB + slot * kSlotB;
+                        const unsigned char *src = img + (size_t)chunk * 2 * kTcPlaneB + (size_t)nt * kRowsB * 128;
                         if (dbg & 2) { bfptx::mbar_arrive(&b_full[slot]); continue; }
-                        bfptx::mbar_arrive_expect_tx(&b_full[slot], (uint32_t)kV2SlotB);
-                        bfptx::bulk_g2s(dst, src, 256 * 128, &b_full[slot]);
-                        bfptx::bulk_g2s(dst + 256 * 128, src + kTcPlaneB, 256 * 128, &b_full[slot]);
+                        bfptx::mbar_arrive_expect_tx(&b_full[slot], kSlotB);
+                        bfptx::bulk_g2s(dst, src, kRowsB * 128, &b_full[slot]);
+                        bfptx::bulk_g2s(dst + kRowsB * 128, src + kTcPlaneB, kRowsB * 128, &b_full[slot]);
                     }
                 }
             }
@@ -665,28 +690,29 @@ __global__ void __launch_bounds__(kV3Threads, 1) mvdr_tc_steer_kernel3(const uns
         // ================= MMA issuer =====================================================================
         {
             // D fp32, A / B fp16, both K-major, M = 128, N = 256
-            const uint32_t idesc = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | ((kRowsB >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t a_base = bfptx::smem_u32(sA), b_base = bfptx::smem_u32(sB);
             uint32_t k = 0, g = 0, w = 0;
             for (int unit = blockIdx.x; unit < units; unit += gridDim.x, w++) {
                 bfptx::mbar_wait(acc_free, (w & 1) ^ 1);
                 tc_fence_after();
-                uint32_t acc0 = 0u, acc1 = 0u;                   // first MMA into N-tile 0 / 1 overwrites
+                uint32_t accm = 0u;                              // bit t set: N-tile t already holds a partial sum
                 for (int ci = 0; ci < kV3Chunks; ci++, g++) {
-                    const int chunk = v3_chunk(ci);
+                    const int chunk = v3_order<QUARTER>(ci);
                     const uint32_t ab = g & 1, aph = (g >> 1) & 1;
                     bfptx::mbar_wait(&a_full[ab], aph);
                     tc_fence_after();
                     const uint64_t da_hi = umma_desc_sw128(a_base + ab * (uint32_t)kV2BufA);
                     const uint64_t da_lo = umma_desc_sw128(a_base + ab * (uint32_t)kV2BufA + (uint32_t)kTcPlaneA);
-                    for (int nt = (chunk < kV3Chunks / 2 ? 0 : 1); nt < 2; nt++, k++) {
-                        const uint32_t slot = k & 1, ph = (k >> 1) & 1;
+                    const int nt0 = QUARTER ? (chunk >> 1) : (chunk < kV3Chunks / 2 ? 0 : 1);
+                    for (int nt = nt0; nt < (QUARTER ? 4 : 2); nt++, k++) {
+                        const uint32_t slot = k % NB, ph = (k / NB) & 1;
                         bfptx::mbar_wait(&b_full[slot], ph);
                         tc_fence_after();
-                        const uint64_t db_hi = umma_desc_sw128(b_base + slot * (uint32_t)kV2SlotB);
-                        const uint64_t db_lo = umma_desc_sw128(b_base + slot * (uint32_t)kV2SlotB + 256u * 128u);
-                        const uint32_t dcol = tmem + (uint32_t)nt * 256u;
-                        const uint32_t acc = nt == 0 ? acc0 : acc1;
+                        const uint64_t db_hi = umma_desc_sw128(b_base + slot * kSlotB);
+                        const uint64_t db_lo = umma_desc_sw128(b_base + slot * kSlotB + kRowsB * 128u);
+                        const uint32_t dcol = tmem + (uint32_t)nt * kRowsB;
+                        const uint32_t acc = (accm >> nt) & 1u;
 #pragma unroll
                         for (int ks = 0; ks < 4; ks++) {
                             const uint64_t ko = (uint64_t)(ks * 2);          // 16 halves = 32 bytes = 2 descriptor units
@@ -694,9 +720,10 @@ __global__ void __launch_bounds__(kV3Threads, 1) mvdr_tc_steer_kernel3(const uns
                             umma_f16_elect(dcol, da_hi + ko, db_lo + ko, idesc, 1u);
                             umma_f16_elect(dcol, da_lo + ko, db_hi + ko, idesc, 1u);
                         }
-                        if (nt == 0) acc0 = 1u; else acc1 = 1u;
+                        accm |= 1u << nt;
                         umma_commit_elect(&b_empty[slot]);
-                        if (nt == 0 && chunk == kV3Chunks / 2 - 1) umma_commit_elect(t0_done);
+                        // columns 0..255 are final after the last item of k-chunk 3 that lands in them
+                        if (chunk == kV3Chunks / 2 - 1 && nt == (QUARTER ? 1 : 0)) umma_commit_elect(t0_done);
                     }
                     umma_commit_elect(&a_empty[ab]);
                 }
@@ -715,9 +742,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) mvdr_tc_steer_kernel3(const uns
             const uint32_t bin = (uint32_t)(lo + f);
             uint32_t p[8], pn[8];                                 // next chunk, the one after (loads two chunks ahead)
 #pragma unroll
-            for (int i = 0; i < 8; i++) p[i] = __ldg(pf + (v3_chunk(0) * 8 + i) * (4 * kTcDirs));
+            for (int i = 0; i < 8; i++) p[i] = __ldg(pf + (v3_order<QUARTER>(0) * 8 + i) * (4 * kTcDirs));
 #pragma unroll
-            for (int i = 0; i < 8; i++) pn[i] = __ldg(pf + (v3_chunk(1) * 8 + i) * (4 * kTcDirs));
+            for (int i = 0; i < 8; i++) pn[i] = __ldg(pf + (v3_order<QUARTER>(1) * 8 + i) * (4 * kTcDirs));
             for (int ci = 0; ci < kV3Chunks; ci++, g++) {
                 const uint32_t ab = g & 1, aph = (g >> 1) & 1;
                 uint32_t c[8];
@@ -725,13 +752,13 @@ __global__ void __launch_bounds__(kV3Threads, 1) mvdr_tc_steer_kernel3(const uns
                 for (int i = 0; i < 8; i++) { c[i] = p[i]; p[i] = pn[i]; }
                 if (ci + 2 < kV3Chunks) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) pn[i] = __ldg(pf + (v3_chunk(ci + 2) * 8 + i) * (4 * kTcDirs));
+                    for (int i = 0; i < 8; i++) pn[i] = __ldg(pf + (v3_order<QUARTER>(ci + 2) * 8 + i) * (4 * kTcDirs));
                 }
                 uint32_t hi[8], lo8[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     float sn, cs;
-                    if (dbg & 1) { sn = 0.25f; cs = 0.75f; } else phasor_fix(bin * c[i], cs, sn);
+                    if (dbg & 1) { sn = 0.25f; cs = 0.75f; } else if (dbg & 4) phasor_fix<false>(bin * c[i], cs, sn); else phasor_fix<true>(bin * c[i], cs, sn);
                     cs *= 256.0f; sn *= 256.0f;
                     const __half2 h = __floats2half2_rn(cs, sn);
                     const float2 hf = __half22float2(h);
@@ -824,7 +851,7 @@ int mvdr_steer_tc(const float2 *d_linv, const double *d_u, int M, int F, int lo,
     int rc = g_image.ensure((size_t)F * kTcChunks * 2 * kTcPlaneB);
     if (rc) return rc;
     if ((rc = g_q.ensure((size_t)F * D * sizeof(float)))) return rc;
-    const int version = getenv("BF_MVDR_TC") ? atoi(getenv("BF_MVDR_TC")) : 3;
+    const int version = getenv("BF_MVDR_TC") ? atoi(getenv("BF_MVDR_TC")) : 4;
     if (version >= 3) {
         static DevBuf expo, colscale;
         if ((rc = expo.ensure((size_t)F * sizeof(int)))) return rc;
@@ -835,7 +862,9 @@ int mvdr_steer_tc(const float2 *d_linv, const double *d_u, int M, int F, int lo,
         BF_CHECK_LAUNCH();
         const int tiles = (D + kTcDirs - 1) / kTcDirs;
         const size_t smem = 2 * kV2BufA + 2 * kV2SlotB + 128;
-        BF_CUDA(cudaFuncSetAttribute(mvdr_tc_steer_kernel3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const bool quarter = version >= 4;
+        BF_CUDA(cudaFuncSetAttribute(mvdr_tc_steer_kernel3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BF_CUDA(cudaFuncSetAttribute(mvdr_tc_steer_kernel3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int units = tiles * F;
         const int grid = units < state().sm_count ? units : state().sm_count;
         {   // fixed-point phase table, rebuilt when the geometry changes
@@ -852,8 +881,12 @@ int mvdr_steer_tc(const float2 *d_linv, const double *d_u, int M, int F, int lo,
             g_phifix = fixbuf.as<uint32_t>();
         }
         const int dbg = getenv("BF_MVDR_DBG") ? atoi(getenv("BF_MVDR_DBG")) : 0;
-        mvdr_tc_steer_kernel3<<<grid, kV3Threads, smem, st>>>(g_image.as<unsigned char>(), g_phifix,
-                                                             colscale.as<float>(), F, lo, D, tiles, g_q.as<float>(), dbg);
+        if (quarter)
+            mvdr_tc_steer_kernel3<true><<<grid, kV3Threads, smem, st>>>(g_image.as<unsigned char>(), g_phifix,
+                                                                       colscale.as<float>(), F, lo, D, tiles, g_q.as<float>(), dbg);
+        else
+            mvdr_tc_steer_kernel3<false><<<grid, kV3Threads, smem, st>>>(g_image.as<unsigned char>(), g_phifix,
+                                                                        colscale.as<float>(), F, lo, D, tiles, g_q.as<float>(), dbg);
         BF_CHECK_LAUNCH();
         mvdr_tc_reduce_kernel<<<(D + 255) / 256, 256, 0, st>>>(g_q.as<float>(), F, D, d_power);
         BF_CHECK_LAUNCH();

@@ -30,6 +30,11 @@ class BfHeatInfo(ctypes.Structure):
                 ("fallback", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
+class BfRecordLayout(ctypes.Structure):
+    """include/bf_b200.h: bf_record_layout (size and member offsets of a shared-memory record)."""
+    _fields_ = [("size", ctypes.c_size_t), ("off", ctypes.c_size_t * 4)]
+
+
 HEAT_INFO_DTYPE = np.dtype([("max_power", "<f4"), ("min_power", "<f4"), ("log_span", "<f4"),
                             ("smooth_max", "<f4"), ("center_col", "<f8"), ("center_row", "<f8"),
                             ("overlay", "<i4"), ("painted", "<i4"), ("fallback", "<i4"),
@@ -95,6 +100,13 @@ def lib():
     L.bf_fd_mvdr_dev_slice.argtypes = [vp, vp, ci, cd, ci, ci, vp]
     L.bf_fd_das_dev_slice.argtypes = [vp, vp, ci, ci, ci, vp]
     L.bf_fd_normalise_dev.argtypes = [vp, ci, ctypes.c_float, ci, vp]
+    L.bf_layout_miso.argtypes = [ci, ci]
+    L.bf_layout_miso.restype = BfRecordLayout
+    L.bf_layout_padata.argtypes = [ci]
+    L.bf_layout_padata.restype = BfRecordLayout
+    L.bf_layout_ring_buffer.argtypes = [ci, ci]
+    L.bf_layout_ring_buffer.restype = BfRecordLayout
+    L.bf_miso_record_listen.argtypes = [vp, vp]
     L.bf_kf_create.restype = vp
     L.bf_kf_destroy.argtypes = [vp]
     L.bf_kf_destroy.restype = None

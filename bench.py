@@ -328,7 +328,7 @@ def mvdr_c4_sharded(torch, dist, nat, L, rank, world, bins=512, dirs=32768, K=64
     Whole-job maps/s = 1 / (slowest rank's time per map, device-timed)."""
     import realtime_scripts.calc_r_prime as rp
     import realtime_scripts.config as cfg
-    from lib.sharded import PeerGather, fd_mvdr_sharded
+    from lib.sharded import PeerGather, fd_mvdr_sharded, fd_mvdr_sharded_bins
     M, N, F = 256, 1024, bins
     res_x, res_y = 256, dirs // 256
     D = res_x * res_y
@@ -354,7 +354,10 @@ def mvdr_c4_sharded(torch, dist, nat, L, rank, world, bins=512, dirs=32768, K=64
         dist.barrier()
         torch.cuda.synchronize()
         a.record()
-        fd_mvdr_sharded(peer, i, snaps, K, 1e-2)
+        if F % world == 0:
+            fd_mvdr_sharded_bins(peer, i, snaps, K, 1e-2, F, dist)      # float64 stages by bins, steering by directions
+        else:
+            fd_mvdr_sharded(peer, i, snaps, K, 1e-2)
         peer.ready(i)
         b.record()
         torch.cuda.synchronize()
@@ -368,7 +371,9 @@ def mvdr_c4_sharded(torch, dist, nat, L, rank, world, bins=512, dirs=32768, K=64
     peer.close()
     ms = float(tt[0])
     return {"workload": "C4 sharded: FD-MVDR, 256 mics, 1024-pt FFT, %d bins, K=%d, %d directions over %d GPUs "
-                        "(%d each), slices exchanged by NVLink peer stores" % (F, K, D, world, (D + world - 1) // world),
+                        "(%d each), slices exchanged by NVLink peer stores%s"
+                        % (F, K, D, world, (D + world - 1) // world,
+                           "; float64 stages sharded by bins, operand images all-gathered (NCCL)" if F % world == 0 else ""),
             "maps_per_s": 1e3 / ms, "ms_per_map": ms, "finite": finite, "n_gpus": world}
 
 

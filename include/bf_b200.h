@@ -233,6 +233,15 @@ int bf_fd_mvdr_dev_slice(const float *d_snapshots, float *d_power, int K, double
 int bf_fd_das_dev_slice(const float *d_signals, float *d_power, int frames, int d_begin, int d_count,
                         void *stream);
 int bf_fd_normalise_dev(float *d_heatmap, int frames, float threshold, int normalise, void *stream);
+/* The same map in two phases, for runs that ALSO shard the float64 stages (31 % of a C4 map's time) by BINS:
+ * bf_fd_mvdr_factor_dev computes spectra, covariance + loading, Cholesky, inverse and the tensor-core operand
+ * images of bins [f_begin, f_begin + f_count) of the band; bf_fd_mvdr_operands exposes the image buffer
+ * (bins x bytes_per_bin bytes) and the per-bin scales (bins floats) so that the ranks can all-gather them
+ * (NCCL over NVLink, lib/sharded.py:fd_mvdr_sharded_bins); bf_fd_mvdr_steer_dev then steers directions
+ * [d_begin, d_begin + d_count) over all bins.  256 microphones (the tcgen05 path) only. */
+int bf_fd_mvdr_factor_dev(const float *d_snapshots, int K, double loading, int f_begin, int f_count, void *stream);
+int bf_fd_mvdr_operands(void **d_image, size_t *bytes_per_bin, void **d_binscale);
+int bf_fd_mvdr_steer_dev(float *d_power, int d_begin, int d_count, void *stream);
 /* device milliseconds of the stages of the last MVDR call: FFT, covariance + loading, Cholesky,
  * triangular inverse, steering contraction */
 int bf_fd_mvdr_timings(float *ms5);

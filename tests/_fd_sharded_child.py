@@ -20,7 +20,7 @@ def main():
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl")
     from lib import _native as nat
-    from lib.sharded import PeerGather, fd_das_sharded, fd_mvdr_sharded
+    from lib.sharded import PeerGather, fd_das_sharded, fd_mvdr_sharded, fd_mvdr_sharded_bins
     import realtime_scripts.calc_r_prime as rp
     import realtime_scripts.config as cfg
     L = nat.lib()
@@ -54,6 +54,15 @@ def main():
         ok = ok and bool(torch.equal(full, got))
         if not torch.equal(full, got):
             print("rank %d mvdr step %d max rel diff %.3e" % (rank, i, float(((full - got).abs() / full).max())))
+    # the float64 stages sharded by bins as well (operand images all-gathered): same map
+    n_bins = 56
+    for i in range(3, 5):
+        fd_mvdr_sharded_bins(pg, i, snaps, K, 1e-2, n_bins, dist)
+        got = pg.maps(i).clone().reshape(-1)
+        torch.cuda.synchronize()
+        ok = ok and bool(torch.equal(full, got))
+        if not torch.equal(full, got):
+            print("rank %d mvdr (bins sharded) step %d max rel diff %.3e" % (rank, i, float(((full - got).abs() / full).max())))
     pg.check()
     dist.barrier()
     pg.close()

@@ -29,6 +29,10 @@ struct FdGeom { int n_mics, n_active, N, lo, hi, D; double fs, c; const double *
 int fd_geometry(FdGeom *g);     // fd_path.cu
 int mvdr_steer_tc(const float2 *d_linv, const double *d_u, int M, int F, int lo, double bin_hz, double inv_c,
                   int D, float *d_power, cudaStream_t st);     // fd_tc.cu
+int mvdr_tc_prepare(const float2 *d_linv, int M, int F, int f0, int fc, cudaStream_t st);      // fd_tc.cu
+int mvdr_tc_steer_only(const double *d_u, int M, int F, int lo, double bin_hz, double inv_c, int D, float *d_power,
+                       cudaStream_t st);                                                      // fd_tc.cu
+int mvdr_tc_operands(void **d_image, size_t *bytes_per_bin, void **d_binscale, int F);         // fd_tc.cu
 
 struct MvdrState {
     DevBuf spec;      // double2 [K][F][M]
@@ -76,11 +80,11 @@ __global__ void mvdr_rfft64_kernel(const float *__restrict__ sig, const int *__r
 // snapshots of the tile's rows and columns go through shared memory 16 at a time.  Same
 // ascending-k order per element; explicit fma (the library is built with --fmad=false).
 __global__ void __launch_bounds__(256) mvdr_cov_tiled_kernel(const double2 *__restrict__ spec, int K, int F, int M,
-                                                             double2 *__restrict__ cov)
+                                                             double2 *__restrict__ cov, int f0)
 {
     constexpr int TB = 64, KC = 16;
     __shared__ double2 xi[KC][TB], xj[KC][TB];
-    const int f = blockIdx.z;
+    const int f = f0 + blockIdx.z;
     const int i0 = blockIdx.y * TB, j0 = blockIdx.x * TB;
     const int ty = threadIdx.y, tx = threadIdx.x, tid = ty * 16 + tx;
     double re[4][4], im[4][4];
@@ -438,9 +442,66 @@ __global__ void __launch_bounds__(TD) mvdr_steer_kernel(const float2 *__restrict
 
 static int ilog2e(int n) { int l = 0; while ((1 << l) < n) l++; return (1 << l) == n ? l : -1; }
 
+// Stages 1-4 for bins [f0, f0 + fc) of the band: float64 FFT of every snapshot (all bins: it is one pass per
+// channel), covariance + loading, Cholesky, triangular inverse -> S.linv[f].  Event i..i+4 time the stages.
+static int mvdr_factor(const float *d_snap, int K, double delta, int f0, int fc, cudaStream_t st, cudaEvent_t *ev,
+                       int *h_fail)
+{
+    FdGeom G;
+    int rc = fd_geometry(&G);
+    if (rc) return rc;
+    const int M = G.n_active, F = G.hi - G.lo;
+    if (M > 1024) { set_error(BF_ERR_CONFIG, "mvdr: at most 1024 microphones"); return BF_ERR_CONFIG; }
+    if (f0 < 0 || fc < 1 || f0 + fc > F) { set_error(BF_ERR_ARG, "mvdr: bin range [%d,+%d) outside the %d-bin band", f0, fc, F); return BF_ERR_ARG; }
+    MvdrState &S = g_mv;
+    if ((rc = S.spec.ensure((size_t)K * F * M * sizeof(double2)))) return rc;
+    if ((rc = S.cov.ensure((size_t)F * M * M * sizeof(double2)))) return rc;
+    if ((rc = S.linv.ensure((size_t)F * M * M * sizeof(float2)))) return rc;
+    static DevBuf work, fail, cov_copy;
+    if ((rc = work.ensure((size_t)F * M * M * sizeof(double2)))) return rc;
+    if ((rc = fail.ensure(sizeof(int)))) return rc;
+    if ((rc = cov_copy.ensure((size_t)F * M * M * sizeof(double2)))) return rc;
+    cudaMemsetAsync(fail.p, 0, sizeof(int), st);
+    const size_t mm = (size_t)M * M;
+    double2 *cov = S.cov.as<double2>() + (size_t)f0 * mm;
+    cudaEventRecord(ev[0], st);
+    const int threads = G.N / 2 < 256 ? (G.N / 2 < 32 ? 32 : G.N / 2) : 256;
+    mvdr_rfft64_kernel<<<dim3(M, K), threads, 2 * G.N * sizeof(double2), st>>>(
+        d_snap, G.active, M, G.n_mics, G.N, ilog2e(G.N), G.lo, G.hi, S.spec.as<double2>());
+    cudaEventRecord(ev[1], st);
+    mvdr_cov_tiled_kernel<<<dim3((M + 63) / 64, (M + 63) / 64, fc), dim3(16, 16), 0, st>>>(
+        S.spec.as<double2>(), K, F, M, S.cov.as<double2>(), f0);
+    mvdr_load_kernel<<<fc, 256, 0, st>>>(cov, M, delta);
+    cudaEventRecord(ev[2], st);
+    S.K = K;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error(BF_ERR_CUDA, "mvdr: %s", cudaGetErrorString(e)); return BF_ERR_CUDA; }
+    // keep a copy of the loaded covariance for bf_fd_get_covariance (the factorisation overwrites it)
+    cudaMemcpyAsync(cov_copy.as<double2>() + (size_t)f0 * mm, cov, (size_t)fc * mm * sizeof(double2), cudaMemcpyDeviceToDevice, st);
+    // blocked float64 factorisation / inverse (one thread per row); BF_MVDR_BLOCKED=0 selects the
+    // column-by-column kernels
+    const bool blocked = M <= 256 && !(getenv("BF_MVDR_BLOCKED") && atoi(getenv("BF_MVDR_BLOCKED")) == 0);
+    const int mt = (M + 31) / 32 * 32;
+    float2 *linv = S.linv.as<float2>() + (size_t)f0 * mm;
+    double2 *wk = work.as<double2>() + (size_t)f0 * mm;
+    if (blocked) mvdr_chol_blocked_kernel<<<fc, mt, 0, st>>>(cov, M, fail.as<int>());
+    else mvdr_chol_kernel<<<fc, 256, 0, st>>>(cov, M, fail.as<int>());
+    cudaEventRecord(ev[3], st);
+    if (blocked) mvdr_trinv_blocked_kernel<<<fc, mt, 0, st>>>(cov, M, linv, wk);
+    else mvdr_trinv_kernel<<<fc, 256, 0, st>>>(cov, M, linv, wk);
+    cudaEventRecord(ev[4], st);
+    // restore the covariance for inspection, then report a failed factorisation
+    cudaMemcpyAsync(cov, cov_copy.as<double2>() + (size_t)f0 * mm, (size_t)fc * mm * sizeof(double2), cudaMemcpyDeviceToDevice, st);
+    e = cudaMemcpyAsync(h_fail, fail.p, sizeof(int), cudaMemcpyDeviceToHost, st);
+    count_launch(5);
+    if (e != cudaSuccess) { set_error(BF_ERR_CUDA, "mvdr: %s", cudaGetErrorString(e)); return BF_ERR_CUDA; }
+    return BF_OK;
+}
+
 // d_count < 0: all directions; otherwise only directions [d_begin, d_begin + d_count) are steered (power[d - d_begin]):
 // the covariance, its factor and the inverse are computed in full on every rank of a direction-sharded run
-// (0.5 % of the work), the steering contraction -- all the rest -- is what shards.
+// (0.5 % of the flops), the steering contraction -- all the rest -- is what shards.  (bf_fd_mvdr_factor_dev /
+// bf_fd_mvdr_steer_dev split the two so that the float64 stages can be sharded by bins as well.)
 int mvdr_dev(const float *d_snap, float *d_power, int K, double delta, cudaStream_t st, int d_begin = 0, int d_count = -1)
 {
     FdGeom G;
@@ -455,51 +516,19 @@ int mvdr_dev(const float *d_snap, float *d_power, int K, double delta, cudaStrea
         G.D = d_count;
     }
     const int M = G.n_active, F = G.hi - G.lo;
-    if (M > 1024) { set_error(BF_ERR_CONFIG, "mvdr: at most 1024 microphones"); return BF_ERR_CONFIG; }
-    MvdrState &S = g_mv;
-    if ((rc = S.spec.ensure((size_t)K * F * M * sizeof(double2)))) return rc;
-    if ((rc = S.cov.ensure((size_t)F * M * M * sizeof(double2)))) return rc;
-    if ((rc = S.linv.ensure((size_t)F * M * M * sizeof(float2)))) return rc;
-    static DevBuf work, fail;
-    if ((rc = work.ensure((size_t)F * M * M * sizeof(double2)))) return rc;
-    if ((rc = fail.ensure(sizeof(int)))) return rc;
-    cudaMemsetAsync(fail.p, 0, sizeof(int), st);
     static cudaEvent_t ev[6] = {nullptr};
     if (!ev[0]) for (int i = 0; i < 6; i++) cudaEventCreate(&ev[i]);
-    cudaEventRecord(ev[0], st);
-    const int threads = G.N / 2 < 256 ? (G.N / 2 < 32 ? 32 : G.N / 2) : 256;
-    mvdr_rfft64_kernel<<<dim3(M, K), threads, 2 * G.N * sizeof(double2), st>>>(
-        d_snap, G.active, M, G.n_mics, G.N, ilog2e(G.N), G.lo, G.hi, S.spec.as<double2>());
-    cudaEventRecord(ev[1], st);
-    mvdr_cov_tiled_kernel<<<dim3((M + 63) / 64, (M + 63) / 64, F), dim3(16, 16), 0, st>>>(
-        S.spec.as<double2>(), K, F, M, S.cov.as<double2>());
-    mvdr_load_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, delta);
-    cudaEventRecord(ev[2], st);
-    S.K = K;
-    // keep a copy of the loaded covariance for bf_fd_get_covariance (work buffer is reused below)
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { set_error(BF_ERR_CUDA, "mvdr: %s", cudaGetErrorString(e)); return BF_ERR_CUDA; }
-    static DevBuf cov_copy;
-    if ((rc = cov_copy.ensure((size_t)F * M * M * sizeof(double2)))) { return rc; }
-    cudaMemcpyAsync(cov_copy.p, S.cov.p, (size_t)F * M * M * sizeof(double2), cudaMemcpyDeviceToDevice, st);
-    // blocked float64 factorisation / inverse (one thread per row); BF_MVDR_BLOCKED=0 selects the
-    // column-by-column kernels
-    const bool blocked = M <= 256 && !(getenv("BF_MVDR_BLOCKED") && atoi(getenv("BF_MVDR_BLOCKED")) == 0);
-    const int mt = (M + 31) / 32 * 32;
-    if (blocked) mvdr_chol_blocked_kernel<<<F, mt, 0, st>>>(S.cov.as<double2>(), M, fail.as<int>());
-    else mvdr_chol_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, fail.as<int>());
-    cudaEventRecord(ev[3], st);
-    if (blocked) mvdr_trinv_blocked_kernel<<<F, mt, 0, st>>>(S.cov.as<double2>(), M, S.linv.as<float2>(), work.as<double2>());
-    else mvdr_trinv_kernel<<<F, 256, 0, st>>>(S.cov.as<double2>(), M, S.linv.as<float2>(), work.as<double2>());
-    cudaEventRecord(ev[4], st);
+    static int *h_fail = nullptr;
+    if (!h_fail) { if (cudaMallocHost(&h_fail, sizeof(int)) != cudaSuccess) { set_error(BF_ERR_CUDA, "mvdr: pinned flag"); return BF_ERR_CUDA; } }
+    *h_fail = 0;
+    if ((rc = mvdr_factor(d_snap, K, delta, 0, F, st, ev, h_fail))) return rc;
+    MvdrState &S = g_mv;
     const double bin_hz = (double)(int)((int)G.fs / 2) / (double)(G.N / 2);
     // steering contraction: tcgen05 tensor-core kernel (fd_tc.cu) for 256 microphones, CUDA-core
     // fp32 kernel otherwise (BF_MVDR_TC=0 forces the latter)
     const bool use_tc = M == 256 && !(getenv("BF_MVDR_TC") && atoi(getenv("BF_MVDR_TC")) == 0);
     if (use_tc) {
-        if ((rc = mvdr_steer_tc(S.linv.as<float2>(), G.u, M, F, G.lo, bin_hz, 1.0 / G.c, G.D, d_power, st))) {
-                        return rc;
-        }
+        if ((rc = mvdr_steer_tc(S.linv.as<float2>(), G.u, M, F, G.lo, bin_hz, 1.0 / G.c, G.D, d_power, st))) return rc;
     } else {
         constexpr int TD = 64, RC = 8;
         const size_t smem = ((size_t)M * TD + (size_t)RC * M) * sizeof(float2);
@@ -508,16 +537,47 @@ int mvdr_dev(const float *d_snap, float *d_power, int K, double delta, cudaStrea
                                                                          bin_hz, 1.0 / G.c, G.D, d_power);
     }
     cudaEventRecord(ev[5], st);
-    e = cudaStreamSynchronize(st);
+    cudaError_t e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) for (int i = 0; i < 5; i++) cudaEventElapsedTime(&g_stage_ms[i], ev[i], ev[i + 1]);
-    int h_fail = 0;
-    if (e == cudaSuccess) e = cudaMemcpy(&h_fail, fail.p, sizeof(int), cudaMemcpyDeviceToHost);
-    // restore the covariance for inspection
-    cudaMemcpy(S.cov.p, cov_copy.p, (size_t)F * M * M * sizeof(double2), cudaMemcpyDeviceToDevice);
-        count_launch(6);
+    count_launch(1);
     if (e != cudaSuccess) { set_error(BF_ERR_CUDA, "mvdr: %s", cudaGetErrorString(e)); return BF_ERR_CUDA; }
-    if (h_fail) { set_error(BF_ERR_CONFIG, "mvdr: covariance not positive definite (increase loading)"); return BF_ERR_CONFIG; }
+    if (*h_fail) { set_error(BF_ERR_CONFIG, "mvdr: covariance not positive definite (increase loading)"); return BF_ERR_CONFIG; }
     return BF_OK;
+}
+
+// ---- two-phase form for runs that shard the float64 stages by BINS (lib/sharded.py:fd_mvdr_sharded_bins) ----
+int mvdr_factor_dev(const float *d_snap, int K, double delta, int f0, int fc, cudaStream_t st)
+{
+    FdGeom G;
+    int rc = fd_geometry(&G);
+    if (rc) return rc;
+    const int M = G.n_active, F = G.hi - G.lo;
+    if (M != 256) { set_error(BF_ERR_CONFIG, "bf_fd_mvdr_factor_dev: the operand images exist for 256 microphones only"); return BF_ERR_CONFIG; }
+    static cudaEvent_t ev[5] = {nullptr};
+    if (!ev[0]) for (int i = 0; i < 5; i++) cudaEventCreate(&ev[i]);
+    static int *h_fail = nullptr;
+    if (!h_fail) { if (cudaMallocHost(&h_fail, sizeof(int)) != cudaSuccess) { set_error(BF_ERR_CUDA, "mvdr: pinned flag"); return BF_ERR_CUDA; } }
+    *h_fail = 0;
+    if ((rc = mvdr_factor(d_snap, K, delta, f0, fc, st, ev, h_fail))) return rc;
+    if ((rc = mvdr_tc_prepare(g_mv.linv.as<float2>(), M, F, f0, fc, st))) return rc;
+    cudaError_t e = cudaStreamSynchronize(st);          // the failure flag is read here: one sync per map
+    if (e != cudaSuccess) { set_error(BF_ERR_CUDA, "mvdr: %s", cudaGetErrorString(e)); return BF_ERR_CUDA; }
+    if (*h_fail) { set_error(BF_ERR_CONFIG, "mvdr: covariance not positive definite (increase loading)"); return BF_ERR_CONFIG; }
+    return BF_OK;
+}
+
+int mvdr_steer_dev(float *d_power, int d_begin, int d_count, cudaStream_t st)
+{
+    FdGeom G;
+    int rc = fd_geometry(&G);
+    if (rc) return rc;
+    if (d_begin < 0 || d_count < 1 || d_begin + d_count > G.D) {
+        set_error(BF_ERR_ARG, "mvdr: direction slice [%d,+%d) outside the %d-direction grid", d_begin, d_count, G.D);
+        return BF_ERR_ARG;
+    }
+    const double bin_hz = (double)(int)((int)G.fs / 2) / (double)(G.N / 2);
+    return mvdr_tc_steer_only(G.u + (size_t)d_begin * G.n_active, G.n_active, G.hi - G.lo, G.lo, bin_hz, 1.0 / G.c,
+                              d_count, d_power, st);
 }
 
 }  // namespace bf
@@ -561,6 +621,33 @@ int bf_fd_mvdr_dev_slice(const float *d_snapshots, float *d_power, int K, double
     if (rc) return rc;
     if (!d_snapshots || !d_power || K < 1 || d_count < 1) { set_error(BF_ERR_ARG, "bf_fd_mvdr_dev_slice: bad arguments"); return BF_ERR_ARG; }
     return mvdr_dev(d_snapshots, d_power, K, loading, (cudaStream_t)stream, d_begin, d_count);
+}
+
+int bf_fd_mvdr_factor_dev(const float *d_snapshots, int K, double loading, int f_begin, int f_count, void *stream)
+{
+    clear_error();
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!d_snapshots || K < 1 || !(loading >= 0.0)) { set_error(BF_ERR_ARG, "bf_fd_mvdr_factor_dev: bad arguments"); return BF_ERR_ARG; }
+    return mvdr_factor_dev(d_snapshots, K, loading, f_begin, f_count, (cudaStream_t)stream);
+}
+
+int bf_fd_mvdr_operands(void **d_image, size_t *bytes_per_bin, void **d_binscale)
+{
+    clear_error();
+    FdGeom G;
+    int rc = fd_geometry(&G);
+    if (rc) return rc;
+    return mvdr_tc_operands(d_image, bytes_per_bin, d_binscale, G.hi - G.lo);
+}
+
+int bf_fd_mvdr_steer_dev(float *d_power, int d_begin, int d_count, void *stream)
+{
+    clear_error();
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!d_power) { set_error(BF_ERR_ARG, "bf_fd_mvdr_steer_dev: bad arguments"); return BF_ERR_ARG; }
+    return mvdr_steer_dev(d_power, d_begin, d_count, (cudaStream_t)stream);
 }
 
 // device time of each stage of the last MVDR call, milliseconds:

@@ -470,10 +470,10 @@ template <bool QUARTER> __device__ __forceinline__ int v3_order(int i) { return 
 // are up to 2^6 below the bin's largest still keep a normal-range lo part, and the absolute error of
 // any element stays <= 2^-25 of the bin's largest entry (cond(R) <= M / loading bounds the spread of the rows).
 __global__ void mvdr_tc_rowscale_kernel(const float2 *__restrict__ linv, int *__restrict__ expo,
-                                        float *__restrict__ binscale)
+                                        float *__restrict__ binscale, int f0)
 {
     __shared__ float red[kTcMics];
-    const int f = blockIdx.x, i = threadIdx.x;                   // 256 threads, one per row
+    const int f = f0 + blockIdx.x, i = threadIdx.x;              // 256 threads, one per row
     const float2 *row = linv + ((size_t)f * kTcMics + i) * kTcMics;
     float mx = 0.0f;
     for (int j = 0; j <= i; j++) { const float2 l = row[j]; mx = fmaxf(mx, fmaxf(fabsf(l.x), fabsf(l.y))); }
@@ -494,9 +494,9 @@ __global__ void mvdr_tc_rowscale_kernel(const float2 *__restrict__ linv, int *__
 
 // image3[f][chunk][plane hi/lo][row n = 2i+part][64 halves]   (k = 2*(j - 32*chunk) + {0: cos, 1: sin})
 __global__ void mvdr_tc_prep3_kernel(const float2 *__restrict__ linv, const int *__restrict__ expo,
-                                     unsigned char *__restrict__ image)
+                                     unsigned char *__restrict__ image, int f0)
 {
-    const int f = blockIdx.y, chunk = blockIdx.x;
+    const int f = f0 + blockIdx.y, chunk = blockIdx.x;
     const float2 *L = linv + (size_t)f * kTcMics * kTcMics;
     unsigned char *img = image + ((size_t)f * kV3Chunks + chunk) * 2 * kTcPlaneB;
     for (int e = threadIdx.x; e < kTcRows * (kV3Kc / 2); e += blockDim.x) {       // one (row, microphone) pair per step
@@ -844,6 +844,81 @@ static int ensure_phi(const double *d_u, int D, int M, double scale, cudaStream_
     return BF_OK;
 }
 
+static DevBuf g_expo, g_binscale;
+
+// Operand images (fp16 hi / lo, pre-swizzled) and per-bin scales of bins [f0, f0 + fc) from their L^-1.
+int mvdr_tc_prepare(const float2 *d_linv, int M, int F, int f0, int fc, cudaStream_t st)
+{
+    if (M != kTcMics) { set_error(BF_ERR_CONFIG, "tensor-core MVDR steering is specialised for 256 microphones (got %d)", M); return BF_ERR_CONFIG; }
+    int rc = g_image.ensure((size_t)F * kTcChunks * 2 * kTcPlaneB);
+    if (rc) return rc;
+    if ((rc = g_expo.ensure((size_t)F * sizeof(int)))) return rc;
+    if ((rc = g_binscale.ensure((size_t)F * sizeof(float)))) return rc;
+    mvdr_tc_rowscale_kernel<<<fc, kTcMics, 0, st>>>(d_linv, g_expo.as<int>(), g_binscale.as<float>(), f0);
+    BF_CHECK_LAUNCH();
+    mvdr_tc_prep3_kernel<<<dim3(kV3Chunks, fc), 256, 0, st>>>(d_linv, g_expo.as<int>(), g_image.as<unsigned char>(), f0);
+    BF_CHECK_LAUNCH();
+    count_launch(2);
+    return BF_OK;
+}
+
+// The buffers a bin-sharded run all-gathers: image = F x bytes_per_bin bytes, binscale = F floats.
+int mvdr_tc_operands(void **d_image, size_t *bytes_per_bin, void **d_binscale, int F)
+{
+    int rc = g_image.ensure((size_t)F * kTcChunks * 2 * kTcPlaneB);
+    if (rc) return rc;
+    if ((rc = g_binscale.ensure((size_t)F * sizeof(float)))) return rc;
+    if ((rc = g_expo.ensure((size_t)F * sizeof(int)))) return rc;
+    if (d_image) *d_image = g_image.p;
+    if (bytes_per_bin) *bytes_per_bin = (size_t)kV3Chunks * 2 * kTcPlaneB;
+    if (d_binscale) *d_binscale = g_binscale.p;
+    return BF_OK;
+}
+
+// Steering contraction over all F bins from the prepared operand images, directions [0, D) of d_u.
+int mvdr_tc_steer_only(const double *d_u, int M, int F, int lo, double bin_hz, double inv_c, int D, float *d_power,
+                       cudaStream_t st)
+{
+    if (M != kTcMics) { set_error(BF_ERR_CONFIG, "tensor-core MVDR steering is specialised for 256 microphones (got %d)", M); return BF_ERR_CONFIG; }
+    if (!g_image.p || !g_binscale.p) { set_error(BF_ERR_NOT_LOADED, "mvdr: no operand images (run the factor stage first)"); return BF_ERR_NOT_LOADED; }
+    int rc = g_q.ensure((size_t)F * D * sizeof(float));
+    if (rc) return rc;
+    const int version = getenv("BF_MVDR_TC") ? atoi(getenv("BF_MVDR_TC")) : 4;
+    const int tiles = (D + kTcDirs - 1) / kTcDirs;
+    const size_t smem = 2 * kV2BufA + 2 * kV2SlotB + 128;
+    const bool quarter = version >= 4;
+    BF_CUDA(cudaFuncSetAttribute(mvdr_tc_steer_kernel3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BF_CUDA(cudaFuncSetAttribute(mvdr_tc_steer_kernel3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int units = tiles * F;
+    const int grid = units < state().sm_count ? units : state().sm_count;
+    {   // fixed-point phase table, rebuilt when the geometry (or the direction slice) changes
+        static DevBuf fixbuf;
+        static uint64_t fix_gen = ~0ull; static double fix_scale = 0.0; static int fix_D = 0;
+        static const double *fix_u = nullptr;                  // a direction slice starts at another row of u
+        if (fix_gen != fd_geometry_generation() || fix_scale != bin_hz * inv_c || fix_D != D || fix_u != d_u) {
+            const size_t cnt = (size_t)tiles * kTcMics * kTcDirs;
+            if ((rc = fixbuf.ensure(cnt * sizeof(uint32_t)))) return rc;
+            mvdr_tc_phifix_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_u, D, bin_hz * inv_c, tiles, fixbuf.as<uint32_t>());
+            BF_CHECK_LAUNCH();
+            fix_gen = fd_geometry_generation(); fix_scale = bin_hz * inv_c; fix_D = D; fix_u = d_u;
+        }
+        g_phifix = fixbuf.as<uint32_t>();
+    }
+    if (lo + F > 1024) { set_error(BF_ERR_CONFIG, "tensor-core MVDR: bin index must stay below 1024"); return BF_ERR_CONFIG; }
+    const int dbg = getenv("BF_MVDR_DBG") ? atoi(getenv("BF_MVDR_DBG")) : 0;
+    if (quarter)
+        mvdr_tc_steer_kernel3<true><<<grid, kV3Threads, smem, st>>>(g_image.as<unsigned char>(), g_phifix,
+                                                                   g_binscale.as<float>(), F, lo, D, tiles, g_q.as<float>(), dbg);
+    else
+        mvdr_tc_steer_kernel3<false><<<grid, kV3Threads, smem, st>>>(g_image.as<unsigned char>(), g_phifix,
+                                                                    g_binscale.as<float>(), F, lo, D, tiles, g_q.as<float>(), dbg);
+    BF_CHECK_LAUNCH();
+    mvdr_tc_reduce_kernel<<<(D + 255) / 256, 256, 0, st>>>(g_q.as<float>(), F, D, d_power);
+    BF_CHECK_LAUNCH();
+    count_launch(3);
+    return BF_OK;
+}
+
 int mvdr_steer_tc(const float2 *d_linv, const double *d_u, int M, int F, int lo, double bin_hz, double inv_c,
                   int D, float *d_power, cudaStream_t st)
 {
@@ -853,45 +928,8 @@ int mvdr_steer_tc(const float2 *d_linv, const double *d_u, int M, int F, int lo,
     if ((rc = g_q.ensure((size_t)F * D * sizeof(float)))) return rc;
     const int version = getenv("BF_MVDR_TC") ? atoi(getenv("BF_MVDR_TC")) : 4;
     if (version >= 3) {
-        static DevBuf expo, colscale;
-        if ((rc = expo.ensure((size_t)F * sizeof(int)))) return rc;
-        if ((rc = colscale.ensure((size_t)F * sizeof(float)))) return rc;
-        mvdr_tc_rowscale_kernel<<<F, kTcMics, 0, st>>>(d_linv, expo.as<int>(), colscale.as<float>());
-        BF_CHECK_LAUNCH();
-        mvdr_tc_prep3_kernel<<<dim3(kV3Chunks, F), 256, 0, st>>>(d_linv, expo.as<int>(), g_image.as<unsigned char>());
-        BF_CHECK_LAUNCH();
-        const int tiles = (D + kTcDirs - 1) / kTcDirs;
-        const size_t smem = 2 * kV2BufA + 2 * kV2SlotB + 128;
-        const bool quarter = version >= 4;
-        BF_CUDA(cudaFuncSetAttribute(mvdr_tc_steer_kernel3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        BF_CUDA(cudaFuncSetAttribute(mvdr_tc_steer_kernel3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int units = tiles * F;
-        const int grid = units < state().sm_count ? units : state().sm_count;
-        {   // fixed-point phase table, rebuilt when the geometry changes
-            static DevBuf fixbuf;
-            static uint64_t fix_gen = ~0ull; static double fix_scale = 0.0; static int fix_D = 0;
-            static const double *fix_u = nullptr;                  // a direction slice starts at another row of u
-            if (fix_gen != fd_geometry_generation() || fix_scale != bin_hz * inv_c || fix_D != D || fix_u != d_u) {
-                const size_t cnt = (size_t)tiles * kTcMics * kTcDirs;
-                if ((rc = fixbuf.ensure(cnt * sizeof(uint32_t)))) return rc;
-                mvdr_tc_phifix_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_u, D, bin_hz * inv_c, tiles, fixbuf.as<uint32_t>());
-                BF_CHECK_LAUNCH();
-                fix_gen = fd_geometry_generation(); fix_scale = bin_hz * inv_c; fix_D = D; fix_u = d_u;
-            }
-            g_phifix = fixbuf.as<uint32_t>();
-        }
-        const int dbg = getenv("BF_MVDR_DBG") ? atoi(getenv("BF_MVDR_DBG")) : 0;
-        if (quarter)
-            mvdr_tc_steer_kernel3<true><<<grid, kV3Threads, smem, st>>>(g_image.as<unsigned char>(), g_phifix,
-                                                                       colscale.as<float>(), F, lo, D, tiles, g_q.as<float>(), dbg);
-        else
-            mvdr_tc_steer_kernel3<false><<<grid, kV3Threads, smem, st>>>(g_image.as<unsigned char>(), g_phifix,
-                                                                        colscale.as<float>(), F, lo, D, tiles, g_q.as<float>(), dbg);
-        BF_CHECK_LAUNCH();
-        mvdr_tc_reduce_kernel<<<(D + 255) / 256, 256, 0, st>>>(g_q.as<float>(), F, D, d_power);
-        BF_CHECK_LAUNCH();
-        count_launch(5);
-        return BF_OK;
+        if ((rc = mvdr_tc_prepare(d_linv, M, F, 0, F, st))) return rc;
+        return mvdr_tc_steer_only(d_u, M, F, lo, bin_hz, inv_c, D, d_power, st);
     }
     mvdr_tc_prep_kernel<<<dim3(kTcChunks, F), 256, 0, st>>>(d_linv, g_image.as<unsigned char>());
     BF_CHECK_LAUNCH();

@@ -100,6 +100,9 @@ def lib():
     L.bf_fd_mvdr_dev_slice.argtypes = [vp, vp, ci, cd, ci, ci, vp]
     L.bf_fd_das_dev_slice.argtypes = [vp, vp, ci, ci, ci, vp]
     L.bf_fd_normalise_dev.argtypes = [vp, ci, ctypes.c_float, ci, vp]
+    L.bf_fd_mvdr_factor_dev.argtypes = [vp, ci, cd, ci, ci, vp]
+    L.bf_fd_mvdr_operands.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(cs), ctypes.POINTER(vp)]
+    L.bf_fd_mvdr_steer_dev.argtypes = [vp, ci, ci, vp]
     L.bf_layout_miso.argtypes = [ci, ci]
     L.bf_layout_miso.restype = BfRecordLayout
     L.bf_layout_padata.argtypes = [ci]

@@ -328,6 +328,32 @@ def fd_mvdr_sharded(peer, i, d_snapshots, K, loading, stream=None):
     peer.scatter(i, part[:, :peer.d_count].contiguous() if peer.d_count else part[:, :0], st)
 
 
+def fd_mvdr_sharded_bins(peer, i, d_snapshots, K, loading, n_bins, dist, stream=None):
+    """Step i of an MVDR map sharded TWICE: the float64 stages (spectra, covariance, Cholesky, inverse, operand
+    images) by BINS -- rank r factors bins [r*B/W, (r+1)*B/W) and the 1 MB-per-bin operand images + per-bin scales
+    are all-gathered over NVLink (two NCCL all-gathers, in place) -- and the steering contraction by DIRECTIONS as
+    in fd_mvdr_sharded.  Needs n_bins divisible by the number of ranks (else use fd_mvdr_sharded).
+    peer.maps(i) is the assembled [1][D] map."""
+    import ctypes
+    torch, nat, L = peer.torch, peer.nat, peer.L
+    world, rank = peer.world, peer.rank
+    if n_bins % world:
+        raise ValueError("fd_mvdr_sharded_bins: %d bins do not divide over %d ranks" % (n_bins, world))
+    st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+    fc = n_bins // world
+    nat.check(L.bf_fd_mvdr_factor_dev(d_snapshots.data_ptr(), K, loading, rank * fc, fc, st))
+    img, per_bin, scale = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_void_p()
+    nat.check(L.bf_fd_mvdr_operands(ctypes.byref(img), ctypes.byref(per_bin), ctypes.byref(scale)))
+    t_img = torch.as_tensor(_DevArray(img.value, (n_bins, per_bin.value), "|u1"), device="cuda")
+    t_scale = torch.as_tensor(_DevArray(scale.value, (n_bins,), "<f4"), device="cuda")
+    dist.all_gather_into_tensor(t_img, t_img[rank * fc:(rank + 1) * fc])          # in place: slice r of the buffer
+    dist.all_gather_into_tensor(t_scale, t_scale[rank * fc:(rank + 1) * fc])
+    part = torch.empty((1, max(peer.d_count, 1)), dtype=torch.float32, device="cuda")
+    if peer.d_count > 0:
+        nat.check(L.bf_fd_mvdr_steer_dev(part.data_ptr(), peer.d_begin, peer.d_count, st))
+    peer.scatter(i, part[:, :peer.d_count].contiguous() if peer.d_count else part[:, :0], st)
+
+
 def fd_das_sharded(peer, i, d_signals, threshold=0.2, normalise=True, stream=None):
     """Step i of direction-sharded frequency-domain DAS for peer.F frames: every rank transforms all channels,
     steers its slice, scatters it; the assembled [F][D] power is normalised like the reference after the

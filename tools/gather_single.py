@@ -1,0 +1,63 @@
+#!/usr/bin/env python3
+"""Run the GATHER instantiation of das_mimo_kernel on ONE GPU (world = 1: own buffer only, step flags on) so that it
+can be captured with ncu (ncu must not wrap a multi-rank command).  C3, pad, 128 frames, a 1/8 direction slice --
+the launch shape of an 8-GPU step.
+
+    python tools/gather_single.py [--slice 8] [--frames 128] [--reps 5]
+"""
+import argparse
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "zybo-rt-sampler-image-detection_b200"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--slice", type=int, default=8)
+    ap.add_argument("--frames", type=int, default=128)
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    import torch
+    from interface import config
+    config.reload(N_MICROPHONES=256, N_SAMPLES=256, MAX_RES_X=180, MAX_RES_Y=180, N_TAPS=8, SKIP_N_MICS=1,
+                  GEOMETRY_N_MICS=256, GEOMETRY_N_ARRAYS=4)
+    from lib import _native as nat, directions
+    L = nat.lib()
+    nat.configure_from(config)
+    directions.load_pad_from_geometry()
+    mics, n = directions.active_microphones()
+    d_mics = torch.from_numpy(nat.i32(mics)).cuda()
+    D, F = 180 * 180, args.frames
+    per = (D + args.slice - 1) // args.slice
+    sig = 0.1 * torch.randn((F, 256, 256), device="cuda")
+    buf = torch.zeros((1, F, per), device="cuda")
+    flags = torch.zeros(8, dtype=torch.int64, device="cuda")
+    timed_out = torch.zeros(1, dtype=torch.int32, device="cuda")
+    vp = ctypes.c_void_p
+    bufs = (vp * 1)(vp(buf.data_ptr()))
+    fl = (vp * 1)(vp(flags.data_ptr()))
+    st = torch.cuda.current_stream().cuda_stream
+    ts = []
+    for i in range(args.reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        nat.check(L.bf_mimo_dev_gather_sync(nat.ALGO_PAD, sig.data_ptr(), F, d_mics.data_ptr(), n, 0, per, 0, 1, bufs, per,
+                                            fl, i, i + 1, timed_out.data_ptr(), st))
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    full = torch.zeros((F, D), device="cuda")
+    nat.check(L.bf_mimo_dev(nat.ALGO_PAD, sig.data_ptr(), full.data_ptr(), F, d_mics.data_ptr(), n, 0, D, None))
+    torch.cuda.synchronize()
+    print({"kernel_ms": float(np.mean(ts[1:])), "flags": int(flags[0]), "timed_out": int(timed_out),
+           "matches_full_launch": bool(torch.equal(full[:, :per], buf[0]))})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,7 +1,6 @@
 """float64 NumPy restatement of the reference's KalmanFilter3D (PC/src/kf.hpp:36-165).
-TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED: the reference needs Eigen, which this image lacks,
-so the C++ could not be compiled here; the product (csrc/kf_host.cu, float32) is checked
-against this restatement to 1e-5."""
+TEST INFRASTRUCTURE ONLY.  Second check beside oracle/ref.py:RefKalman (the reference's own class compiled
+against oracle/eigen_shim): the product (csrc/kf_host.cu, float32) is checked against this restatement to 1e-5."""
 import numpy as np
 
 

@@ -244,3 +244,40 @@ class RefReceiver:
             a.close()
             b.close()
         return out.reshape(self.M, self.N)
+
+
+class RefKalman:
+    """The reference's KalmanFilter3D (PC/src/kf.hpp, compiled unmodified against oracle/eigen_shim -- Eigen itself
+    is absent here -- behind oracle/kf_ref_wrap.cpp).  Same three calls as PC/src/kf.pyx:18-46."""
+
+    PATH = os.path.join(ROOT, "default", "libkf_ref.so")
+
+    @staticmethod
+    def available():
+        return os.path.exists(RefKalman.PATH)
+
+    def __init__(self):
+        self.L = ctypes.CDLL(RefKalman.PATH)
+        self.L.kfref_create.restype = ctypes.c_void_p
+        for f in (self.L.kfref_destroy, self.L.kfref_update, self.L.kfref_get_state, self.L.kfref_predict):
+            f.restype = None
+        self.h = ctypes.c_void_p(self.L.kfref_create())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.kfref_destroy(self.h)
+            self.h = None
+
+    def update(self, m):
+        a = np.ascontiguousarray(m, np.float32)
+        self.L.kfref_update(self.h, _p(a))
+
+    def get_state(self):
+        out = np.zeros(3, np.float32)
+        self.L.kfref_get_state(self.h, _p(out))
+        return out
+
+    def predict(self, n):
+        out = np.zeros(3, np.float32)
+        self.L.kfref_predict(self.h, ctypes.c_int(int(n)), _p(out))
+        return out

@@ -31,6 +31,39 @@ def test_kalman_filter_matches_oracle():
     assert np.allclose(kf.get_state(), [2.9707165, 3.8292835, 0.0], atol=1e-5)
 
 
+def test_kalman_filter_matches_the_reference_class():
+    """The product's filter (csrc/kf_host.cu behind lib.kf.CyKF) against the REFERENCE's own KalmanFilter3D --
+    PC/src/kf.hpp compiled unmodified (oracle/build_ref.py:build_kf) against a minimal stand-in for Eigen, which
+    this image lacks (oracle/eigen_shim: plain-loop fixed-size matrices).  Pinned: the reference's matrices, its
+    update / predict equations and the quirk of predict() (the transition matrix is re-multiplied every step).
+    Not pinned: Eigen's own evaluation order inside a 6x6 product, hence a float32 tolerance, not bit equality."""
+    from oracle import ref
+    if not ref.RefKalman.available():
+        pytest.skip("oracle/_ref/default/libkf_ref.so not built")
+    from lib.kf import CyKF
+    rng = np.random.default_rng(12)
+    kf, rk = CyKF(), ref.RefKalman()
+    assert np.array_equal(rk.get_state(), np.zeros(3, np.float32))
+    pos = np.array([-3.0, 8.0, 1.0])
+    worst = 0.0
+    for k in range(300):
+        pos = pos + np.array([0.2, 0.05, -0.01]) + (4.0 if k == 150 else 0.0)
+        m = (pos + rng.normal(0, 0.4, 3)).astype(np.float32)
+        kf.update(list(m))
+        rk.update(m)
+        a, b = kf.get_state(), rk.get_state()
+        worst = max(worst, float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0))))
+        if k % 29 == 0:
+            for n in (0, 1, 2, 3, 5):
+                assert np.allclose(kf.predict(n), rk.predict(n), rtol=2e-5, atol=2e-5), (k, n)
+    assert worst <= 2e-6, worst
+    # the reference's own debug sequence (kf.hpp:170-176) through the reference's own class
+    rk = ref.RefKalman()
+    for m in [(1, 1, 0), (2, 2, 0), (3, 4, 0)]:
+        rk.update(m)
+    assert np.allclose(rk.get_state(), [2.9707165, 3.8292835, 0.0], atol=1e-5)
+
+
 # ---- capture files -------------------------------------------------------------------------------
 def _udp_frame(payload, src_port=21844, dst_port=21844):
     udp = struct.pack(">HHHH", src_port, dst_port, 8 + len(payload), 0) + payload

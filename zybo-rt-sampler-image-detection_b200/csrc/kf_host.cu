@@ -4,8 +4,9 @@
 // as lib.kf.CyKF): a linear constant-velocity filter on (x, y, z) in float32 with
 // A = [[I, I], [0, I]], Q = 0.1 I6, H = [I3 0], R = 0.1 I3, P0 = I6, x0 = 0.  It smooths the
 // arg-max of the power map before it is turned into a steering offset (visual.py:64-72).
-// The reference needs Eigen (absent from this image, so it cannot be compiled here: PARITY
-// UNPINNED, checked against a float64 NumPy restatement to 1e-5); plain loops here.
+// The reference needs Eigen, absent from this image; the test suite compiles the reference's header unmodified
+// against a minimal stand-in (oracle/eigen_shim) and this file agrees with it to 2e-6 relative over 300 updates
+// (tests/test_tracking_and_capture.py); plain loops here.
 // predict(N) keeps the reference's quirk: the transition applied in step i is A^(i+1)
 // (kf.hpp:121-125 multiplies An by A after every step).
 #include <string.h>

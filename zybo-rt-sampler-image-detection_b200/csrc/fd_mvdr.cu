@@ -240,7 +240,11 @@ __global__ void mvdr_trinv_kernel(const double2 *__restrict__ chol, int M, float
 static constexpr int kNB = 8;       // panel width
 static constexpr int kKC = 64;      // k-chunk staged in shared memory
 
-__global__ void __launch_bounds__(256) mvdr_chol_blocked_kernel(double2 *__restrict__ cov, int M, int *__restrict__ fail)
+// Register budget (measured, C4: 512 bins): __launch_bounds__(256, 1) lets ptxas keep the unrolled row loads in flight
+// (128 registers, 2 CTAs per SM): Cholesky 1.75 ms, inverse 1.83 ms.  Capped at 64 registers for 4 CTAs per SM (all 512
+// bins in one wave) they take 1.82 / 2.43 ms, at the 80-88 registers ptxas picks unprompted 2.08 / 2.31 ms: these loops
+// are bound by load latency per thread, not by the number of resident CTAs.
+__global__ void __launch_bounds__(256, 1) mvdr_chol_blocked_kernel(double2 *__restrict__ cov, int M, int *__restrict__ fail)
 {
     double2 *R = cov + (size_t)blockIdx.x * M * M;
     __shared__ double2 pan[kNB][kKC];          // L[j0+c][k0 .. k0+KC)
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(256) mvdr_chol_blocked_kernel(double2 *__restr
 }
 
 // Z = L^-1, row panels of NB: thread c owns column c, acc[r] = sum_{k < i0} L[i0+r][k] Z[k][c]
-__global__ void __launch_bounds__(256) mvdr_trinv_blocked_kernel(const double2 *__restrict__ chol, int M,
+__global__ void __launch_bounds__(256, 1) mvdr_trinv_blocked_kernel(const double2 *__restrict__ chol, int M,
                                                                   float2 *__restrict__ linv, double2 *__restrict__ work)
 {
     const double2 *Lt = chol + (size_t)blockIdx.x * M * M;

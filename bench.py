@@ -864,8 +864,11 @@ def main():
             shard_note = {"equal_slice_kernel_ms": [float(x) for x in tk], "directions_per_rank": [c for _, c in bounds]}
             del probe
         try:
-            peer = PeerGather(D, F, rank, world, dist, depth=int(os.environ.get("BF_GATHER_DEPTH", "2")),
-                              bounds=bounds)   # kernel stores into every rank's buffer
+            # overlap: the steps of the timed loop are launched back to back from inputs already resident, each into
+            # its own buffer of the ring -- step i + 1 may take over SMs while step i runs its last tiles
+            overlap = os.environ.get("BF_GATHER_OVERLAP", "1") != "0" and args.algo == "pad"
+            peer = PeerGather(D, F, rank, world, dist, depth=int(os.environ.get("BF_GATHER_DEPTH", "4" if overlap else "2")),
+                              bounds=bounds, overlap=overlap)   # kernel stores into every rank's buffer
             d_maps = torch.zeros((F, D), device="cuda")
             fs, ds = D, 1
         except RuntimeError as e:               # raised on every rank together: fall back to the NCCL route
@@ -907,10 +910,15 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall = time.perf_counter()
+    per_step_events = not (peer and peer.overlap)    # an event between two launches would serialise them again
+    ev_begin = torch.cuda.Event(enable_timing=True)
+    ev_begin.record()
     for i in range(args.steps):
-        ev[i][0].record()
+        if per_step_events:
+            ev[i][0].record()
         step(args.warmup + i)
-        ev[i][1].record()
+        if per_step_events:
+            ev[i][1].record()
     if pipe:
         pipe.finish()                 # the last gathers are part of the timed region
     if peer:
@@ -920,9 +928,9 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall
     launches = int(L.bf_kernel_launches(0))
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    # whole timed region on the device as well (first start -> last stop)
-    span_ms = ev[0][0].elapsed_time(ev_end)
+    # whole timed region on the device (first start -> last stop)
+    span_ms = ev_begin.elapsed_time(ev_end)
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev) if per_step_events else span_ms
     t = torch.tensor([dev_ms, span_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -324,6 +324,14 @@ int bf_mimo_dev_gather_sync(int algo, const float *d_signals, int frames, const 
                             int d_begin, int d_count, int rank, int world, void *const *gather_bufs,
                             long per_rank, void *const *flag_arrays, long long wait_seq, long long signal_seq,
                             int *d_timed_out, void *stream);
+/* Overlapping steps (pad, bf_mimo_dev_gather_sync with signal_seq > 0): on = 1 launches every following step with
+ * programmatic stream serialisation -- its CTAs take over SMs as the CTAs of the previous kernel on the stream exit,
+ * so a run of back-to-back steps has no idle SMs in the last round of tiles, no launch gap and no prologue between
+ * steps.  The caller promises (a) consecutive steps store to different buffers (a PeerGather of depth >= 2 does) and
+ * (b) a step's inputs were complete before the PREVIOUS kernel on the stream was launched (nothing that produces
+ * them is enqueued between two steps).  Work enqueued AFTER a step still sees it, and everything before it,
+ * complete.  on = 0 (default): ordinary stream order.  on < 0: query.  Returns the previous setting. */
+int bf_gather_overlap(int on);
 int bf_gather_signal(void *const *flag_arrays /* host array of `world` device pointers */, int world, int rank,
                      long long step, void *stream);
 int bf_gather_wait(const void *d_my_flags, int world, long long step, int *d_timed_out, void *stream);

@@ -37,8 +37,9 @@ def main():
     sig = 0.1 * torch.randn((steps, F, M, N), generator=gen, device="cuda")
     d_mics = torch.from_numpy(mics).cuda()
     ok = True
-    for algo in (nat.ALGO_PAD, nat.ALGO_LERP):
-        pg = PeerGather(D, F, rank, world, dist, depth=3, consume_lag=1)
+    # third pass: pad with overlapping steps (programmatic stream serialisation, bf_gather_overlap)
+    for algo, overlap in ((nat.ALGO_PAD, False), (nat.ALGO_LERP, False), (nat.ALGO_PAD, True)):
+        pg = PeerGather(D, F, rank, world, dist, depth=3, consume_lag=1, overlap=overlap)
         got = []
         for i in range(steps):
             pg.step(i, algo, sig[i], d_mics, n)

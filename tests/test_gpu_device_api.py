@@ -399,6 +399,57 @@ def test_streaming_replay_of_a_wire_format_recording():
     assert bits_equal(odd["maps"].cpu().numpy(), want[1::2])
 
 
+def test_overlapping_gather_steps_on_one_gpu():
+    """bf_gather_overlap: back-to-back steps of the fused gather kernel launched with programmatic stream
+    serialisation (step i + 1 takes over SMs while step i runs its last tiles), world = 1 with the step flags on, a
+    ring of 3 buffers, several frame counts (so that the last round of tiles is ragged): every step's maps == the
+    plain launch, bit for bit; the setting is sticky until switched off and does not leak into other launches."""
+    import ctypes
+    config, nat, L = _setup("c1")
+    torch = _torch()
+    from lib import directions
+    g = gold("c1")
+    mics = nat.i32(g["mic_ids"])
+    D, n, N, M = 400, 64, 256, 64
+    whole, _ = directions.whole_and_f32()
+    L.load_coefficients_pad(nat.ptr(whole), whole.size)
+    nat.check()
+    d_mics = torch.from_numpy(mics).cuda()
+    vp = ctypes.c_void_p
+    st = torch.cuda.current_stream().cuda_stream
+    seq = 0
+    flags = torch.zeros(8, dtype=torch.int64, device="cuda")
+    timed_out = torch.zeros(1, dtype=torch.int32, device="cuda")
+    fl = (vp * 1)(vp(flags.data_ptr()))
+    for F, d0, dc, steps, depth in ((37, 0, 400, 9, 3), (150, 96, 250, 6, 3), (3, 8, 392, 12, 4)):
+        gen = torch.Generator(device="cuda").manual_seed(F)
+        sig = 0.1 * torch.randn((steps, F, M, N), generator=gen, device="cuda")
+        ring = [torch.full((1, F, dc), float("nan"), device="cuda") for _ in range(depth)]
+        got = []
+        torch.cuda.synchronize()
+        assert L.bf_gather_overlap(1) == 0
+        for i in range(steps):
+            seq += 1
+            bufs = (vp * 1)(vp(ring[i % depth].data_ptr()))
+            nat.check(L.bf_mimo_dev_gather_sync(nat.ALGO_PAD, sig[i].data_ptr(), F, d_mics.data_ptr(), n, d0, dc, 0, 1,
+                                                bufs, dc, fl, max(0, seq - depth + 1), seq, timed_out.data_ptr(), st))
+            if i >= depth - 1:                      # the buffer about to be reused: copy it out (ordinary stream order)
+                got.append(ring[(i + 1) % depth][0].clone())
+        assert L.bf_gather_overlap(0) == 1 and L.bf_gather_overlap(-1) == 0
+        torch.cuda.synchronize()
+        assert int(timed_out) == 0 and int(flags[0]) == seq
+        # steps whose buffer was not reused are still in the ring
+        first_kept = steps - (depth - 1)
+        want = torch.zeros((steps, F, D), device="cuda")
+        for i in range(steps):
+            nat.check(L.bf_mimo_dev(nat.ALGO_PAD, sig[i].data_ptr(), want[i].data_ptr(), F, d_mics.data_ptr(), n, 0, D, None))
+        torch.cuda.synchronize()
+        for j, m in enumerate(got):                 # got[j] = step j (copied out before step j + depth reused its buffer)
+            assert torch.equal(m, want[j][:, d0:d0 + dc]), (F, j)
+        for i in range(max(first_kept, len(got)), steps):
+            assert torch.equal(ring[i % depth][0], want[i][:, d0:d0 + dc]), (F, i)
+
+
 def test_batch_replay_windows_and_maps():
     """BASELINE config C5 mechanics at C1 size: 30 fps windows at floor(k*fs/30) of a channel-major
     recording -> gather kernel -> batched maps == one mimo_pad call per NumPy-sliced window."""

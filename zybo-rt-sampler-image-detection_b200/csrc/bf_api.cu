@@ -458,15 +458,17 @@ int bf_mimo_dev_gather_sync(int algo, const float *d_signals, int frames, const 
     }
     ImgLayout lay{};
     if (wait_seq > 0 || signal_seq > 0) {
-        if ((rc = S.d_done_counter.ensure(sizeof(unsigned int)))) return rc;
+        if ((rc = S.d_done_counter.ensure(4 * sizeof(unsigned int)))) return rc;
         static bool zeroed = false;
-        if (!zeroed) { BF_CUDA(cudaMemset(S.d_done_counter.p, 0, sizeof(unsigned int))); zeroed = true; }
+        if (!zeroed) { BF_CUDA(cudaMemset(S.d_done_counter.p, 0, 4 * sizeof(unsigned int))); zeroed = true; }
         lay.flags_local = (long long *)flag_arrays[rank];
         lay.wait_seq = wait_seq;
         lay.signal_seq = signal_seq;
         lay.world = world;
         lay.flag_rank = rank;
-        lay.done_counter = S.d_done_counter.as<unsigned int>();
+        // two steps can be in flight when they overlap: the ticket counter rotates with the step number
+        lay.done_counter = S.d_done_counter.as<unsigned int>() + (signal_seq & 3);
+        lay.overlap = (S.gather_overlap && algo == BF_ALGO_PAD && signal_seq > 0) ? 1 : 0;
         lay.timed_out = d_timed_out;
         for (int r = 0; r < world; r++) lay.flags_all[r] = (long long *)flag_arrays[r];
     }
@@ -482,6 +484,15 @@ int bf_mimo_dev_gather_sync(int algo, const float *d_signals, int frames, const 
         else lay.peers[lay.n_peers++] = dst;
     }
     return mimo_tiled(algo, d_signals, own, frames, d_mic_ids, n, d_begin, d_count, lay, (cudaStream_t)stream);
+}
+
+int bf_gather_overlap(int on)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    State &S = state();
+    const int was = S.gather_overlap;
+    if (on >= 0) S.gather_overlap = on ? 1 : 0;
+    return was;
 }
 
 int bf_miso_dev(int algo, const float *d_signals, float *d_out, int blocks, const int *d_mic_ids,

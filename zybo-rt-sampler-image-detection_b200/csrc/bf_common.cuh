@@ -90,7 +90,8 @@ struct State {
     int exact_sum = 1;
     int sm_count = 0;
     int device = -1;
-    DevBuf d_done_counter;       // last-CTA ticket of the fused gather kernel
+    DevBuf d_done_counter;       // last-CTA tickets of the fused gather kernel (4: overlapping steps rotate)
+    int gather_overlap = 0;      // bf_gather_overlap
 };
 
 State &state();
@@ -112,6 +113,10 @@ struct ImgLayout {
     long long *flags_local; long long wait_seq;
     long long *flags_all[8]; int world, flag_rank; long long signal_seq;
     unsigned int *done_counter; int *timed_out;
+    // launch with programmatic stream serialisation: the kernel's CTAs may take over SMs while the previous kernel
+    // of the stream is still running its last tiles (consecutive steps must not touch the same output locations and
+    // the inputs must be complete before the PREVIOUS launch: see bf_gather_overlap in bf_b200.h)
+    int overlap;
 };
 int mimo_tiled(int algo, const float *d_sig, float *d_img, int frames, const int *d_mics, int n,
                int d_begin, int d_count, ImgLayout lay, cudaStream_t st);   // das_mimo.cu

@@ -94,6 +94,7 @@ def lib():
     L.bf_ipc_close.argtypes = [vp]
     L.bf_mimo_dev_gather.argtypes = [ci, vp, ci, vp, ci, ci, ci, ci, ci, vp, ctypes.c_long, vp]
     L.bf_mimo_dev_gather_sync.argtypes = [ci, vp, ci, vp, ci, ci, ci, ci, ci, vp, ctypes.c_long, vp, cll, cll, vp, vp]
+    L.bf_gather_overlap.argtypes = [ci]
     L.bf_gather_signal.argtypes = [vp, ci, ci, cll, vp]
     L.bf_gather_wait.argtypes = [vp, ci, cll, vp, vp]
     L.bf_peer_scatter.argtypes = [vp, ctypes.c_long, ci, ci, ci, vp, ctypes.c_long, vp]

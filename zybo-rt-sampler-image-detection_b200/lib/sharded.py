@@ -139,13 +139,17 @@ class PeerGather:
     depth >= consume_lag + 2).  maps(i) is the assembled [F][D] tensor of step i.
     """
 
-    def __init__(self, n_directions, frames, rank, world, dist, depth=2, consume_lag=0, bounds=None):
+    def __init__(self, n_directions, frames, rank, world, dist, depth=2, consume_lag=0, bounds=None, overlap=False):
         """bounds: optional list of (d_begin, d_count) per rank (weighted_bounds) instead of equal slices; the
-        gather buffers are sized for the largest slice and maps() drops the padding."""
+        gather buffers are sized for the largest slice and maps() drops the padding.
+        overlap: launch the steps so that step i + 1 may take over SMs while step i still runs its last tiles
+        (bf_gather_overlap in bf_b200.h; pad only).  The caller promises that the inputs of a step are complete
+        before the previous step is launched -- nothing that produces them is enqueued between two step() calls."""
         import ctypes
         if depth < consume_lag + 2:
             raise ValueError("PeerGather: depth must be at least consume_lag + 2")
         self.consume_lag = consume_lag
+        self.overlap = bool(overlap)
         import torch
         from . import _native
         self.torch, self.nat, self.L = torch, _native, _native.lib()
@@ -242,9 +246,16 @@ class PeerGather:
         self._seq_of[i] = seq
         k = i % self.depth
         wait_seq = max(0, seq - self.depth + 1 + self.consume_lag)
-        nat.check(L.bf_mimo_dev_gather_sync(algo, d_signals.data_ptr(), self.F, d_mic_ids.data_ptr(), n,
-                                            self.d_begin, self.d_count, self.rank, self.world, self._buf_arrays[k],
-                                            self.per, self._flag_array, wait_seq, seq, self.timed_out.data_ptr(), st))
+        if self.overlap:
+            L.bf_gather_overlap(1)
+        try:
+            nat.check(L.bf_mimo_dev_gather_sync(algo, d_signals.data_ptr(), self.F, d_mic_ids.data_ptr(), n,
+                                                self.d_begin, self.d_count, self.rank, self.world,
+                                                self._buf_arrays[k], self.per, self._flag_array, wait_seq, seq,
+                                                self.timed_out.data_ptr(), st))
+        finally:
+            if self.overlap:
+                L.bf_gather_overlap(0)
 
     def scatter(self, i, d_slice, stream=None):
         """Step i for a producer that does not store to the peers itself (the frequency-domain maps): d_slice is

@@ -845,14 +845,16 @@ def main():
         bounds = None
         if os.environ.get("BF_SHARD_WEIGHTED", "1") != "0":
             # the GPUs of a node do not all run at the same clock under load and a step is as fast as its slowest
-            # rank: time this rank's equal slice alone, share the times, and size the slices by measured speed
-            probe = torch.zeros((F, per), device="cuda")
+            # rank: time this GPU on a launch without tile rounding (all directions, 32 frames: contiguous unit
+            # ranges, every CTA gets the same work), share the times, and size the slices by measured speed
+            Fp = min(F, 32)
+            probe = torch.zeros((Fp, D), device="cuda")
             ts = []
-            for i in range(4):
+            for i in range(5):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                nat.check(L.bf_mimo_dev_ex(algo, d_pool[i % pool].data_ptr(), probe.data_ptr(), F, d_mics.data_ptr(), n,
-                                           d_begin, max(d_count, 1), per, 1, d_begin, None))
+                nat.check(L.bf_mimo_dev_ex(algo, d_pool[i % pool].data_ptr(), probe.data_ptr(), Fp, d_mics.data_ptr(), n,
+                                           0, D, D, 1, 0, None))
                 b.record()
                 torch.cuda.synchronize()
                 ts.append(a.elapsed_time(b))
@@ -861,7 +863,8 @@ def main():
             dist.all_reduce(tk, op=dist.ReduceOp.SUM)
             bounds = weighted_bounds(D, [1.0 / float(x) for x in tk])
             d_begin, d_count = bounds[rank]
-            shard_note = {"equal_slice_kernel_ms": [float(x) for x in tk], "directions_per_rank": [c for _, c in bounds]}
+            shard_note = {"probe_ms_all_directions_%d_frames" % Fp: [float(x) for x in tk],
+                          "directions_per_rank": [c for _, c in bounds]}
             del probe
         try:
             # overlap: the steps of the timed loop are launched back to back from inputs already resident, each into
@@ -911,6 +914,8 @@ def main():
     barrier()
     t_wall = time.perf_counter()
     per_step_events = not (peer and peer.overlap)    # an event between two launches would serialise them again
+    if peer and os.environ.get("BF_RENDEZVOUS", "1") != "0":
+        peer.rendezvous()             # all GPUs enter the timed region together (the host barrier leaves them skewed)
     ev_begin = torch.cuda.Event(enable_timing=True)
     ev_begin.record()
     for i in range(args.steps):

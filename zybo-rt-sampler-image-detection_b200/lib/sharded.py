@@ -277,6 +277,16 @@ class PeerGather:
                                         self._buf_arrays[k], self.per, st))
         nat.check(L.bf_gather_signal(self._flag_array, self.world, self.rank, seq, st))
 
+    def rendezvous(self, stream=None):
+        """Device-side barrier over the step flags: every rank publishes one (empty) step and its stream waits for
+        everyone's.  After a host barrier the ranks still leave it tens to hundreds of microseconds apart; with this
+        in front of a timed run all GPUs start their first step together."""
+        st = stream if stream is not None else self.torch.cuda.current_stream().cuda_stream
+        self._seq += 1
+        self.nat.check(self.L.bf_gather_signal(self._flag_array, self.world, self.rank, self._seq, st))
+        self.nat.check(self.L.bf_gather_wait(self.flags[self.rank], self.world, self._seq,
+                                             self.timed_out.data_ptr(), st))
+
     def ready(self, i, stream=None):
         """Make the stream wait until every rank's slice of step i has arrived; returns the
         [world][F][per] view of that step."""

@@ -275,7 +275,7 @@ def test_host_batch_replay_equals_per_buffer_calls(algo_name, pinned):
     L.load_coefficients_pad(nat.ptr(whole), whole.size)
     L.load_coefficients_lerp(nat.ptr(d32), d32.size)
     nat.check()
-    F = 37                                            # chunk schedule 4 + 17 + 16 (small first chunk, ragged)
+    F = 37                                            # chunk schedule 4 + 29 + 4 (small first and last chunk, ragged)
     rng = np.random.default_rng(21)
     frames = rng.standard_normal((F, M, N)).astype(np.float32)
     frames[3] = g["signals"]

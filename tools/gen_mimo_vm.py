@@ -26,7 +26,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "..", "zybo-rt-sampler-image-detection_b200", "csrc", "das_mimo_vm.inc")
 
 
-def gen(J, lerp, shared, carry=False, fastbr=False, weave=False, late=False):
+def gen(J, lerp, shared, carry=False, fastbr=False, weave=False, late=False, pair=False):
     """PTX text of one chunk loop.  Operands: %0 .. %(R*Q-1) accumulators (r*Q+q, .b64),
     then [U_0..U_{Q-1} if shared], then eptr (+r), rowp (+r), micb (r), rowb (r).
 
@@ -37,7 +37,13 @@ def gen(J, lerp, shared, carry=False, fastbr=False, weave=False, late=False):
     weave:  (with carry) the next entry's row pair q is loaded right behind the adds that consumed pair q of
             the current entry, in the order the next handler will use them, instead of all at the end.
     late:   (without carry) row pair q is loaded just before its adds instead of all rows up front --
-            fewer live registers (lerp at 96 registers)."""
+            fewer live registers (lerp at 96 registers).
+    pair:   (pad; measured, NOT shipped) handler code 10 = this entry AND the next one are uniform: both rows are
+            added in one handler (same order per accumulator), one decode and one branch for two entries; needs a
+            table builder that marks the pairs greedily inside every chunk.  12 333 against 12 796 maps/s without
+            the marks on the same box: ptxas gives the 64-add block its own accumulator allocation and ends it
+            with 28 register moves, and wraps the second predicated branch of every dispatch in BSSY / BSYNC."""
+    assert not (pair and lerp)
     Q = J // 2
     nacc = R * Q
     nU = Q if shared else 0
@@ -57,7 +63,9 @@ def gen(J, lerp, shared, carry=False, fastbr=False, weave=False, late=False):
         a(f".reg .b64 DA<{Q}>, DB<{Q}>, T;")
         a(f".reg .b32 w<{R}>;")
         a(f".reg .b64 W<{R}>;")
-    a("TS: .branchtargets HU, H1, H2, H3, H4, H5, H6, H7, HG, HEND;")
+    if pair:
+        a(".reg .pred pv;")
+    a("TS: .branchtargets HU, H1, H2, H3, H4, H5, H6, H7, HG, HEND%s;" % (", HV" if pair else ""))
 
     def load_rows(ptr, t, d):
         for j in range(J):
@@ -126,6 +134,9 @@ def gen(J, lerp, shared, carry=False, fastbr=False, weave=False, late=False):
             first_rows()
         a("and.b32 hc, ey, 0xff;")
         if fastbr:
+            if pair:
+                a("setp.eq.u32 pv, hc, 10;")
+                a("@pv bra.uni HV;")
             a("setp.eq.u32 pu, hc, 0;")
             a("@pu bra.uni HU;")
         a("brx.idx.uni hc, TS;")
@@ -134,15 +145,15 @@ def gen(J, lerp, shared, carry=False, fastbr=False, weave=False, late=False):
     dispatch()
 
     # ---- uniform: one delay for all 8 directions ----------------------------------------
-    def uniform_adds(q):
+    def uniform_adds(q, P="A", DP="DA"):
         if shared:
-            a(f"add.rn.f32x2 {U(q)}, {U(q)}, A{q};")
+            a(f"add.rn.f32x2 {U(q)}, {U(q)}, {P}{q};")
             if lerp:
                 for r in range(R):
-                    a(f"fma.rn.f32x2 {acc(r, q)}, W{r}, DA{q}, {acc(r, q)};")
+                    a(f"fma.rn.f32x2 {acc(r, q)}, W{r}, {DP}{q}, {acc(r, q)};")
         else:
             for r in range(R):
-                accumulate(r, q, "A", "DA")
+                accumulate(r, q, P, DP)
 
     a("HU:")
     if carry and weave:
@@ -182,6 +193,24 @@ def gen(J, lerp, shared, carry=False, fastbr=False, weave=False, late=False):
         advance()
         for q in range(Q):
             uniform_adds(q)
+        dispatch()
+
+    # ---- two uniform entries in a row (pad): rows of entry i in ta, of entry i + 1 in tb --------
+    if pair:
+        a("HV:")
+        if not carry:
+            first_rows()
+        pack("ta", "A")
+        advance()                                   # word of entry i + 1 (uniform: only its offset is used)
+        a("and.b32 pb, ex, 0xffff;")
+        a(f"add.u32 pb, pb, {o_rowp};")
+        load_rows("pb", "tb", "db")
+        for q in range(Q):
+            uniform_adds(q)
+        pack("tb", "B")
+        advance()                                   # word of entry i + 2
+        for q in range(Q):
+            uniform_adds(q, "B", "DB")
         dispatch()
 
     # ---- two runs: directions [0, s) use delay a, [s, 8) delay b ------------------------

@@ -37,9 +37,15 @@ def main():
     sig = 0.1 * torch.randn((steps, F, M, N), generator=gen, device="cuda")
     d_mics = torch.from_numpy(mics).cuda()
     ok = True
-    # third pass: pad with overlapping steps (programmatic stream serialisation, bf_gather_overlap)
-    for algo, overlap in ((nat.ALGO_PAD, False), (nat.ALGO_LERP, False), (nat.ALGO_PAD, True)):
-        pg = PeerGather(D, F, rank, world, dist, depth=3, consume_lag=1, overlap=overlap)
+    # third pass: pad with overlapping steps (programmatic stream serialisation, bf_gather_overlap); fourth: ragged
+    # slices whose sizes are not multiples of the 8-direction group (the buffers' row stride is padded)
+    ragged = [(0, D // world + 3)] + [(D // world + 3 + (r - 1) * ((D - D // world - 3) // (world - 1)),
+                                       (D - D // world - 3) // (world - 1)) for r in range(1, world)]
+    ragged[-1] = (ragged[-1][0], D - ragged[-1][0])
+    for algo, overlap, bounds in ((nat.ALGO_PAD, False, None), (nat.ALGO_LERP, False, None), (nat.ALGO_PAD, True, None),
+                                  (nat.ALGO_PAD, True, ragged)):
+        pg = PeerGather(D, F, rank, world, dist, depth=3, consume_lag=1, overlap=overlap, bounds=bounds)
+        assert pg.per % 8 == 0
         got = []
         for i in range(steps):
             pg.step(i, algo, sig[i], d_mics, n)

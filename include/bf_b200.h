@@ -171,6 +171,10 @@ int bf_miso_dev(int algo, const float *d_signals, float *d_out, int blocks,
  * complete.  Same result as `frames` successive mimo_pad / mimo_lerp calls. */
 int bf_mimo_host_batch(int algo, const float *signals, float *images, int frames,
                        const int *adaptive_array, int n);
+/* The chunk sizes bf_mimo_host_batch uses for `frames` frames (host logic only, no device needed): small chunks
+ * at both ends -- the first H2D copy and the last D2H copy are the two the call cannot overlap with a kernel --
+ * and up to 32 frames in between.  Writes at most `capacity` sizes, returns the number of chunks (-1: bad argument). */
+int bf_host_batch_schedule(int frames, int *chunk_frames, int capacity);
 
 /* ---- tables straight from device memory -------------------------------
  * algo PAD: d_table = int32 [count]; LERP/HYBRID: float32 delays [count];
@@ -324,6 +328,15 @@ int bf_mimo_dev_gather_sync(int algo, const float *d_signals, int frames, const 
                             int d_begin, int d_count, int rank, int world, void *const *gather_bufs,
                             long per_rank, void *const *flag_arrays, long long wait_seq, long long signal_seq,
                             int *d_timed_out, void *stream);
+/* Launch plan of the tiled power-map kernel, host logic only (no device needed; for tests and tools): a launch
+ * of `groups` direction groups (8 directions each) x `frames` frames on `sm_count` SMs runs `grid` CTAs of
+ * `consumer_warps` + 1 warps; ranges = 1: every CTA owns a contiguous range of (frame, group) units, 0: whole tiles
+ * handed out round-robin.  bf_mimo_walk lists the tiles CTA `block` processes, in order, as (frame, first group,
+ * groups) triples (at most `capacity` of them are written) and returns their number, or -1 on a bad argument. */
+int bf_mimo_plan(int lerp, int groups, int frames, int overlap, int sm_count, int *consumer_warps, int *grid,
+                 int *ranges);
+long bf_mimo_walk(int lerp, int groups, int frames, int overlap, int sm_count, int block, int *tiles, long capacity);
+
 /* Overlapping steps (pad, bf_mimo_dev_gather_sync with signal_seq > 0): on = 1 launches every following step with
  * programmatic stream serialisation -- its CTAs take over SMs as the CTAs of the previous kernel on the stream exit,
  * so a run of back-to-back steps has no idle SMs in the last round of tiles, no launch gap and no prologue between

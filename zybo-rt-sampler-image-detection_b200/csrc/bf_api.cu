@@ -511,6 +511,38 @@ int bf_miso_dev(int algo, const float *d_signals, float *d_out, int blocks, cons
     return miso_run(algo, d_signals, d_out, blocks, d_mic_ids, n, offset, 0, scale, (cudaStream_t)stream);
 }
 
+// Chunk schedule of bf_mimo_host_batch: ramp up and down.  What the call cannot hide is the H2D copy of the FIRST
+// chunk (nothing to run yet) and the D2H copy of the LAST one (nothing left to run): 4-frame chunks at both ends
+// (1 MB in, 0.5 MB out at C3: ~70 us together instead of ~400 us for 16 / 32 frames), 12-frame chunks next to them
+// on long batches, chunks of up to 32 frames in between.  Short launches are not inefficient: the kernel hands out
+// equal unit ranges (TileWalk), so a 4-frame launch has no ragged last round.
+static void host_batch_schedule(int frames, std::vector<int> &c_start, std::vector<int> &c_size)
+{
+    std::vector<int> head, tail;
+    if (frames > 8 && frames < 64) { head = {4}; tail = {4}; }
+    else if (frames >= 64) { head = {4, 12}; tail = {12, 4}; }
+    int used = 0;
+    for (int v : head) used += v;
+    for (int v : tail) used += v;
+    const int mid = frames - used;
+    const int nmid = (mid + 31) / 32;
+    int f = 0;
+    auto push = [&](int take) { if (take > 0) { c_start.push_back(f); c_size.push_back(take); f += take; } };
+    for (int v : head) push(v);
+    for (int i = 0; i < nmid; i++) push(mid / nmid + (i < mid % nmid ? 1 : 0));
+    for (int v : tail) push(v);
+}
+
+int bf_host_batch_schedule(int frames, int *chunk_frames, int capacity)
+{
+    if (frames < 1) return -1;
+    std::vector<int> c_start, c_size;
+    host_batch_schedule(frames, c_start, c_size);
+    for (size_t i = 0; i < c_size.size() && (int)i < capacity; i++)
+        if (chunk_frames) chunk_frames[i] = c_size[i];
+    return (int)c_size.size();
+}
+
 int bf_mimo_host_batch(int algo, const float *signals, float *images, int frames,
                        const int *adaptive_array, int n)
 {
@@ -526,27 +558,8 @@ int bf_mimo_host_batch(int algo, const float *signals, float *images, int frames
     }
     const size_t sig_f = (size_t)S.cfg.n_microphones * S.cfg.n_samples;     // floats per frame
     const int D = S.cfg.max_res_x * S.cfg.max_res_y;
-    // chunk schedule: ramp up and down.  What the call cannot hide is the H2D copy of the FIRST chunk (nothing to
-    // run yet) and the D2H copy of the LAST one (nothing left to run): 4-frame chunks at both ends (1 MB in, 0.5 MB
-    // out at C3: ~70 us together instead of ~400 us for 16 / 32 frames), 12-frame chunks next to them on long
-    // batches, chunks of up to 32 frames in between.  Short launches are no longer inefficient: the kernel hands
-    // out equal unit ranges (TileWalk), so a 4-frame launch has no ragged last round.  `chunk` = largest one.
     std::vector<int> c_start, c_size;
-    {
-        std::vector<int> head, tail;
-        if (frames > 8 && frames < 64) { head = {4}; tail = {4}; }
-        else if (frames >= 64) { head = {4, 12}; tail = {12, 4}; }
-        int used = 0;
-        for (int v : head) used += v;
-        for (int v : tail) used += v;
-        const int mid = frames - used;
-        const int nmid = (mid + 31) / 32;
-        int f = 0;
-        auto push = [&](int take) { if (take > 0) { c_start.push_back(f); c_size.push_back(take); f += take; } };
-        for (int v : head) push(v);
-        for (int i = 0; i < nmid; i++) push(mid / nmid + (i < mid % nmid ? 1 : 0));
-        for (int v : tail) push(v);
-    }
+    host_batch_schedule(frames, c_start, c_size);
     int chunk = 0;
     for (int v : c_size) chunk = v > chunk ? v : chunk;
     static cudaStream_t st_in = nullptr, st_run = nullptr, st_out = nullptr;

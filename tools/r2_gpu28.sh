@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-2 GPU call 28 (1 GPU): whole GPU suite, default bench line, ncu re-captures of das_mimo (sources changed: tile
+# round-2 GPU calls 28 and 33 (1 GPU): whole GPU suite, default bench line, ncu re-captures of das_mimo (sources changed: tile
 # hand-out + overlapping steps) and the launch list of the bench command
 cd "$(dirname "$0")/.."
 O=gpurun_out

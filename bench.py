@@ -654,7 +654,7 @@ def e2e_sharded(torch, dist, nat, L, algo, d_pool, d_mics, n, D, F, M, N, rank, 
     fused kernel + NVLink peer stores, and rank 0 copies the assembled [F][D] maps device -> host.  All copies
     are inside the timed region; H2D + input gather of step i+1 and D2H of step i-1 overlap the kernel of step i
     (three streams).  Returns maps/s (max over ranks) or None when peer memory is unavailable."""
-    from lib.sharded import PeerGather
+    from lib.sharded import PeerGather, PeerInput
     try:
         peer = PeerGather(D, F, rank, world, dist, depth=4, consume_lag=1, bounds=bounds)
     except RuntimeError:
@@ -663,11 +663,20 @@ def e2e_sharded(torch, dist, nat, L, algo, d_pool, d_mics, n, D, F, M, N, rank, 
     n_host = min(d_pool.shape[0], 3)
     split = F % world == 0                      # otherwise every rank copies the whole batch itself
     Fp = F // world if split else F
+    # input all-gather: NCCL by default; BF_E2E_INPUT=p2p uses the copy engines over NVLink peer memory instead
+    # (lib.sharded.PeerInput: no SMs needed).  Measured the same at 8 GPUs (83.1-83.6 k against 84.6 k maps/s): this
+    # leg is bound by rank 0's host side (~25 driver calls per 1.2 ms step from Python), not by the gather.
+    pin = None
+    if split and os.environ.get("BF_E2E_INPUT", "nccl") == "p2p":
+        try:
+            pin = PeerInput((Fp, M, N), rank, world, dist, slots=2)
+        except RuntimeError:
+            pin = None
     h_in = torch.empty((n_host, Fp, M, N), dtype=torch.float32).pin_memory()
     h_in.copy_(d_pool[:n_host, rank * Fp:(rank + 1) * Fp].cpu() if split else d_pool[:n_host].cpu())
     h_out = torch.empty((2, F, D), dtype=torch.float32).pin_memory() if rank == 0 else None
-    d_in = torch.empty((2, F, M, N), device="cuda")
-    d_part = torch.empty((2, Fp, M, N), device="cuda") if split else None
+    d_in = pin.views if pin else torch.empty((2, F, M, N), device="cuda")
+    d_part = torch.empty((2, Fp, M, N), device="cuda") if split and not pin else None
     d_asm = torch.empty((2, F, D), device="cuda") if rank == 0 else None
     s_in, s_run, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
     ev_in = [torch.cuda.Event() for _ in range(2)]
@@ -682,7 +691,11 @@ def e2e_sharded(torch, dist, nat, L, algo, d_pool, d_mics, n, D, F, M, N, rank, 
             with torch.cuda.stream(s_in):
                 if j >= 2:
                     s_in.wait_event(ev_run[sl])                  # the kernel that read this slot has finished
-                if split:
+                    if pin:
+                        peer.ready(i - 2, s_in.cuda_stream)      # ... on EVERY rank (its step flag is published)
+                if pin:
+                    pin.push(sl, h_in[i % n_host], s_in.cuda_stream)
+                elif split:
                     d_part[sl].copy_(h_in[i % n_host], non_blocking=True)
                     dist.all_gather_into_tensor(d_in[sl], d_part[sl])        # NVLink; stream-ordered behind the copy
                 else:
@@ -690,6 +703,8 @@ def e2e_sharded(torch, dist, nat, L, algo, d_pool, d_mics, n, D, F, M, N, rank, 
                 ev_in[sl].record(s_in)
             with torch.cuda.stream(s_run):
                 s_run.wait_event(ev_in[sl])
+                if pin:
+                    pin.wait(sl, s_run.cuda_stream)              # every rank's frames of this step have arrived
                 peer.step(i, algo, d_in[sl], d_mics, n, s_run.cuda_stream)
                 ev_run[sl].record(s_run)
                 if rank == 0 and j >= 1:                         # consume step i-1 behind the launch of step i
@@ -734,10 +749,15 @@ def e2e_sharded(torch, dist, nat, L, algo, d_pool, d_mics, n, D, F, M, N, rank, 
     t = torch.tensor([dt], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.barrier()
+    if pin:
+        pin.check()
+        pin.close()
     peer.close()
     return {"value": steps * F / float(t[0]), "unit": "maps/s", "steps": steps,
             "h2d_bytes_per_step_per_rank": Fp * frame_bytes, "h2d_bytes_per_step": F * frame_bytes if split else world * F * frame_bytes,
-            "input_gather": "NCCL all-gather of the F frames over NVLink (%d frames per rank over PCIe)" % Fp if split else None,
+            "input_gather": ("copy-engine all-gather of the F frames over NVLink peer memory (%d frames per rank over PCIe)" % Fp
+                             if pin else "NCCL all-gather of the F frames over NVLink (%d frames per rank over PCIe)" % Fp)
+            if split else None,
             "d2h_bytes_per_step_rank0": F * D * 4, "host_maps_bit_exact_vs_one_gpu": ok,
             "api": "host batch in (pinned, F/world frames per rank) -> input all-gather -> bf_mimo_dev_gather_sync (this "
                    "rank's direction slice, peer stores) -> assembled maps out to the host on rank 0; copies inside the "
@@ -1086,7 +1106,10 @@ def main():
             e2e["sharded"] = sh
 
         # ---- extra: BASELINE config C5 (bounded sample), then C2 and C4 -----------------------
-        if world > 1 and args.workload == "c3":
+        rest = os.environ.get("BF_EXTRAS") != "e2e"            # tools: BF_EXTRAS=e2e stops after the end-to-end legs
+        if not rest:
+            pass
+        elif world > 1 and args.workload == "c3":
             frames_r, ms_r, err_r = 0, 0.0, None
             stream_r = None
             try:
@@ -1124,18 +1147,18 @@ def main():
             except Exception as e:  # noqa: BLE001
                 replay = {"error": str(e)}
         mvdr_sh = None
-        if world > 1 and peer is not None:               # every rank: direction-sharded C4 (peer memory available)
+        if rest and world > 1 and peer is not None:      # every rank: direction-sharded C4 (peer memory available)
             try:
                 mvdr_sh = mvdr_c4_sharded(torch, dist, nat, L, rank, world)
             except Exception as ex:  # noqa: BLE001
                 mvdr_sh = {"error": str(ex)}
-        if rank == 0 and args.workload == "c3":
+        if rest and rank == 0 and args.workload == "c3":
             try:
                 hm = d_maps if (world == 1 or peer) else d_maps[:D].t().contiguous()   # [F][D] maps of the last step
                 heat = heatmap_c5(torch, hm, hbm_peak)
             except Exception as e:  # noqa: BLE001
                 heat = {"error": str(e)}
-        if rank == 0:
+        if rest and rank == 0:
             try:
                 miso = miso_c2(args, nat, L, config, directions, torch, stream, hbm_peak)
             except Exception as e:  # noqa: BLE001

@@ -328,6 +328,11 @@ int bf_mimo_dev_gather_sync(int algo, const float *d_signals, int frames, const 
                             int d_begin, int d_count, int rank, int world, void *const *gather_bufs,
                             long per_rank, void *const *flag_arrays, long long wait_seq, long long signal_seq,
                             int *d_timed_out, void *stream);
+/* Asynchronous copy between device buffers of this GPU and of a peer (a pointer from bf_ipc_open) on the copy
+ * engines (no SMs: it proceeds while a persistent kernel occupies the whole GPU).  Used by lib/sharded.py:PeerInput
+ * for the all-gather of the INPUT frames of a sharded step; follow it with bf_gather_signal. */
+int bf_peer_copy(void *dst, const void *src, size_t bytes, void *stream);
+
 /* Launch plan of the tiled power-map kernel, host logic only (no device needed; for tests and tools): a launch
  * of `groups` direction groups (8 directions each) x `frames` frames on `sm_count` SMs runs `grid` CTAs of
  * `consumer_warps` + 1 warps; ranges = 1: every CTA owns a contiguous range of (frame, group) units, 0: whole tiles

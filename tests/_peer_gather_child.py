@@ -61,6 +61,38 @@ def main():
             ok = ok and bool(torch.equal(full, got[i]))
         dist.barrier()
         pg.close()
+    # input all-gather on the copy engines (PeerInput): every rank pushes its frames of a step, all ranks end up
+    # with the whole batch; slots are reused only after every rank's kernel of the step that used them finished
+    from lib.sharded import PeerInput
+    Fp = 3
+    whole = 0.1 * torch.randn((steps, world * Fp, M, N), generator=gen, device="cuda")      # same on every rank
+    h_parts = whole[:, rank * Fp:(rank + 1) * Fp].cpu().pin_memory()
+    pin = PeerInput((Fp, M, N), rank, world, dist, slots=2)
+    pg = PeerGather(D, world * Fp, rank, world, dist, depth=3, consume_lag=1)
+    s_in = torch.cuda.Stream()
+    got = []
+    for i in range(steps):
+        sl = i & 1
+        if i >= 2:
+            pg.ready(i - 2, s_in.cuda_stream)
+        pin.push(sl, h_parts[i], s_in.cuda_stream)
+        batch = pin.wait(sl)
+        ok = ok and bool(torch.equal(batch, whole[i]))
+        pg.step(i, nat.ALGO_PAD, batch, d_mics, n)
+        if i >= 1:
+            got.append(pg.maps(i - 1).clone())
+    got.append(pg.maps(steps - 1).clone())
+    torch.cuda.synchronize()
+    pin.check()
+    pg.check()
+    for i in range(steps):
+        full = torch.zeros((world * Fp, D), device="cuda")
+        nat.check(L.bf_mimo_dev(nat.ALGO_PAD, whole[i].data_ptr(), full.data_ptr(), world * Fp, d_mics.data_ptr(), n, 0, D, None))
+        torch.cuda.synchronize()
+        ok = ok and bool(torch.equal(full, got[i]))
+    dist.barrier()
+    pin.close()
+    pg.close()
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

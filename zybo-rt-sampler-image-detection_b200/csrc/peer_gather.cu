@@ -84,6 +84,20 @@ extern "C" int bf_peer_scatter(const float *d_src, long count, int frames, int r
     return BF_OK;
 }
 
+// Copy between device buffers of this GPU and of a peer (opened with bf_ipc_open): cudaMemcpyAsync, i.e. the copy
+// engines over NVLink -- no SMs, so it runs while a persistent kernel holds every SM (a collective kernel would wait
+// for the gap between two launches).
+extern "C" int bf_peer_copy(void *dst, const void *src, size_t bytes, void *stream)
+{
+    clear_error();
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!dst || !src) { set_error(BF_ERR_ARG, "bf_peer_copy: null pointer"); return BF_ERR_ARG; }
+    if (bytes == 0) return BF_OK;
+    BF_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return BF_OK;
+}
+
 extern "C" int bf_dev_alloc(size_t bytes, void **d_ptr)
 {
     clear_error();

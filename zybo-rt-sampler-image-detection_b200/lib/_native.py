@@ -95,6 +95,7 @@ def lib():
     L.bf_mimo_dev_gather.argtypes = [ci, vp, ci, vp, ci, ci, ci, ci, ci, vp, ctypes.c_long, vp]
     L.bf_mimo_dev_gather_sync.argtypes = [ci, vp, ci, vp, ci, ci, ci, ci, ci, vp, ctypes.c_long, vp, cll, cll, vp, vp]
     L.bf_gather_overlap.argtypes = [ci]
+    L.bf_peer_copy.argtypes = [vp, vp, ctypes.c_size_t, vp]
     L.bf_host_batch_schedule.argtypes = [ci, vp, ci]
     L.bf_mimo_plan.argtypes = [ci, ci, ci, ci, ci, vp, vp, vp]
     L.bf_mimo_walk.argtypes = [ci, ci, ci, ci, ci, ci, vp, ctypes.c_long]

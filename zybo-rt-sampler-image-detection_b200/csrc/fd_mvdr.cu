@@ -239,14 +239,28 @@ __global__ void mvdr_trinv_kernel(const double2 *__restrict__ chol, int M, float
 // the NB pivot rows are broadcast from shared memory.  Same arithmetic, different summation order.
 static constexpr int kNB = 8;       // panel width
 static constexpr int kKC = 64;      // k-chunk staged in shared memory
+// The streamed operand (a thread's own row of L / column of Z, 16 bytes per k) comes from L2 at ~500 cycles a load;
+// four loads in flight per thread (what the registers allow) leave the FP64 pipe idle most of the time.  Each thread
+// therefore prefetches its own values through a private lane of a shared-memory ring with cp.async -- kSub k's per
+// group, two groups in flight, no registers held and no barrier (a thread only reads what it copied itself).
+static constexpr int kSub = 8;
+static constexpr int kRingBytes = 2 * kSub * 256 * (int)sizeof(double2);      // 64 KB per CTA, dynamic
+__device__ __forceinline__ void cp_async16_cg(void *dst_smem, const void *src_gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bfptx::smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Register budget (measured, C4: 512 bins): __launch_bounds__(256, 1) lets ptxas keep the unrolled row loads in flight
 // (128 registers, 2 CTAs per SM): Cholesky 1.75 ms, inverse 1.83 ms.  Capped at 64 registers for 4 CTAs per SM (all 512
 // bins in one wave) they take 1.82 / 2.43 ms, at the 80-88 registers ptxas picks unprompted 2.08 / 2.31 ms: these loops
 // are bound by load latency per thread, not by the number of resident CTAs.
-__global__ void __launch_bounds__(256, 1) mvdr_chol_blocked_kernel(double2 *__restrict__ cov, int M, int *__restrict__ fail)
+__global__ void __launch_bounds__(256, 2) mvdr_chol_blocked_kernel(double2 *__restrict__ cov, int M, int *__restrict__ fail)
 {
     double2 *R = cov + (size_t)blockIdx.x * M * M;
+    extern __shared__ __align__(16) unsigned char ring_raw[];
+    double2 *ring = (double2 *)ring_raw;       // [2][kSub][256]: this thread's prefetched L[i][k]
     __shared__ double2 pan[kNB][kKC];          // L[j0+c][k0 .. k0+KC)
     __shared__ double2 lrow[kNB];              // L[j0+c'][j] of the column being finished
     __shared__ double pivot;
@@ -273,14 +287,27 @@ __global__ void __launch_bounds__(256, 1) mvdr_chol_blocked_kernel(double2 *__re
             }
             __syncthreads();
             if (live) {
-#pragma unroll 4
-                for (int kk = 0; kk < kc; kk++) {
-                    const double2 a = R[(size_t)(k0 + kk) * M + i];
+                // kc is a multiple of kSub (j0 and kKC are multiples of 8)
+                const int nsub = kc / kSub;
+                auto issue = [&](int sb) {
 #pragma unroll
-                    for (int c = 0; c < kNB; c++) {
-                        const double2 b = pan[c][kk];
-                        sx[c] = fma(-a.x, b.x, fma(-a.y, b.y, sx[c]));
-                        sy[c] = fma(-a.y, b.x, fma(a.x, b.y, sy[c]));
+                    for (int kk = 0; kk < kSub; kk++)
+                        cp_async16_cg(&ring[((sb & 1) * kSub + kk) * 256 + i], &R[(size_t)(k0 + sb * kSub + kk) * M + i]);
+                    cp_async_commit();
+                };
+                issue(0);
+                for (int sb = 0; sb < nsub; sb++) {
+                    if (sb + 1 < nsub) { issue(sb + 1); cp_async_wait<1>(); }
+                    else cp_async_wait<0>();
+#pragma unroll
+                    for (int kk = 0; kk < kSub; kk++) {
+                        const double2 a = ring[((sb & 1) * kSub + kk) * 256 + i];
+#pragma unroll
+                        for (int c = 0; c < kNB; c++) {
+                            const double2 b = pan[c][sb * kSub + kk];
+                            sx[c] = fma(-a.x, b.x, fma(-a.y, b.y, sx[c]));
+                            sy[c] = fma(-a.y, b.x, fma(a.x, b.y, sy[c]));
+                        }
                     }
                 }
             }
@@ -322,12 +349,14 @@ __global__ void __launch_bounds__(256, 1) mvdr_chol_blocked_kernel(double2 *__re
 }
 
 // Z = L^-1, row panels of NB: thread c owns column c, acc[r] = sum_{k < i0} L[i0+r][k] Z[k][c]
-__global__ void __launch_bounds__(256, 1) mvdr_trinv_blocked_kernel(const double2 *__restrict__ chol, int M,
+__global__ void __launch_bounds__(256, 2) mvdr_trinv_blocked_kernel(const double2 *__restrict__ chol, int M,
                                                                   float2 *__restrict__ linv, double2 *__restrict__ work)
 {
     const double2 *Lt = chol + (size_t)blockIdx.x * M * M;
     double2 *Z = work + (size_t)blockIdx.x * M * M;
     float2 *Zf = linv + (size_t)blockIdx.x * M * M;
+    extern __shared__ __align__(16) unsigned char ring_raw[];
+    double2 *ring = (double2 *)ring_raw;       // [2][kSub][256]: this thread's prefetched Z[k][c]
     __shared__ double2 pan[kNB][kKC];          // L[i0+r][k0 .. k0+KC)
     __shared__ double2 tri[kNB][kNB];          // L[i0+r][i0+r']
     const int c = threadIdx.x;
@@ -346,15 +375,27 @@ __global__ void __launch_bounds__(256, 1) mvdr_trinv_blocked_kernel(const double
             }
             __syncthreads();
             if (c < M && cw < k0 + kc) {
-                const int kb = max(0, cw - k0);
-#pragma unroll 4
-                for (int kk = kb; kk < kc; kk++) {
-                    const double2 z = Z[(size_t)(k0 + kk) * M + c];
+                // Z[k][c] = 0 for k < cw (cw is a multiple of 32, hence of kSub): start at the warp's first column
+                const int sb0 = max(0, cw - k0) / kSub, nsub = kc / kSub;
+                auto issue = [&](int sb) {
 #pragma unroll
-                    for (int r = 0; r < kNB; r++) {
-                        const double2 a = pan[r][kk];
-                        ax[r] = fma(a.x, z.x, fma(-a.y, z.y, ax[r]));
-                        ay[r] = fma(a.x, z.y, fma(a.y, z.x, ay[r]));
+                    for (int kk = 0; kk < kSub; kk++)
+                        cp_async16_cg(&ring[((sb & 1) * kSub + kk) * 256 + c], &Z[(size_t)(k0 + sb * kSub + kk) * M + c]);
+                    cp_async_commit();
+                };
+                issue(sb0);
+                for (int sb = sb0; sb < nsub; sb++) {
+                    if (sb + 1 < nsub) { issue(sb + 1); cp_async_wait<1>(); }
+                    else cp_async_wait<0>();
+#pragma unroll
+                    for (int kk = 0; kk < kSub; kk++) {
+                        const double2 z = ring[((sb & 1) * kSub + kk) * 256 + c];
+#pragma unroll
+                        for (int r = 0; r < kNB; r++) {
+                            const double2 a = pan[r][sb * kSub + kk];
+                            ax[r] = fma(a.x, z.x, fma(-a.y, z.y, ax[r]));
+                            ay[r] = fma(a.x, z.y, fma(a.y, z.x, ay[r]));
+                        }
                     }
                 }
             }
@@ -488,10 +529,16 @@ static int mvdr_factor(const float *d_snap, int K, double delta, int f0, int fc,
     const int mt = (M + 31) / 32 * 32;
     float2 *linv = S.linv.as<float2>() + (size_t)f0 * mm;
     double2 *wk = work.as<double2>() + (size_t)f0 * mm;
-    if (blocked) mvdr_chol_blocked_kernel<<<fc, mt, 0, st>>>(cov, M, fail.as<int>());
+    if (blocked) {
+        BF_CUDA(cudaFuncSetAttribute(mvdr_chol_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes));
+        mvdr_chol_blocked_kernel<<<fc, mt, kRingBytes, st>>>(cov, M, fail.as<int>());
+    }
     else mvdr_chol_kernel<<<fc, 256, 0, st>>>(cov, M, fail.as<int>());
     cudaEventRecord(ev[3], st);
-    if (blocked) mvdr_trinv_blocked_kernel<<<fc, mt, 0, st>>>(cov, M, linv, wk);
+    if (blocked) {
+        BF_CUDA(cudaFuncSetAttribute(mvdr_trinv_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes));
+        mvdr_trinv_blocked_kernel<<<fc, mt, kRingBytes, st>>>(cov, M, linv, wk);
+    }
     else mvdr_trinv_kernel<<<fc, 256, 0, st>>>(cov, M, linv, wk);
     cudaEventRecord(ev[4], st);
     // restore the covariance for inspection, then report a failed factorisation

@@ -112,3 +112,24 @@ def test_weighted_bounds_tile_the_grid():
         assert np.all(np.abs(share - np.array(w) / np.sum(w)) <= 8 / D + 1e-9)
     eq = weighted_bounds(32400, [1.0] * 8)
     assert max(c for _, c in eq) - min(c for _, c in eq) <= 8
+
+
+def test_gather_layout_rows_are_32_byte_aligned():
+    """Row stride of the fused gather buffers: the largest slice rounded up to 8 directions, whatever the slicing
+    (a warp's 8 results are one 32-byte peer store), and the slices must tile the grid in rank order."""
+    import pytest
+    from lib.sharded import gather_layout, shard_bounds, weighted_bounds
+    for D, world in ((32400, 8), (32400, 2), (400, 2), (169, 3), (1824, 8), (7, 4)):
+        bounds, per = gather_layout(D, world)
+        assert bounds == [shard_bounds(D, world, r)[1:] for r in range(world)]
+        assert per % 8 == 0 and per >= max(c for _, c in bounds) and per - max(c for _, c in bounds) < 8
+        assert sum(c for _, c in bounds) == D
+    assert gather_layout(32400, 8)[1] == 4056                       # 4050 directions per rank -> rows of 4056 floats
+    wb = weighted_bounds(32400, [1.0, 1.01, 0.99, 1.0, 1.0, 1.0, 1.02, 0.98])
+    bounds, per = gather_layout(32400, 8, wb)
+    assert bounds == wb and per % 8 == 0 and per >= max(c for _, c in wb)
+    ragged, per = gather_layout(400, 2, [(0, 203), (203, 197)])
+    assert per == 208
+    for bad in ([(0, 200), (201, 199)], [(0, 200)], [(1, 199), (200, 200)], [(0, 300), (300, 101)]):
+        with pytest.raises(ValueError):
+            gather_layout(400, 2, bad)

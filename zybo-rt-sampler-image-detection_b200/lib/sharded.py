@@ -39,6 +39,24 @@ def weighted_bounds(n_directions, weights, multiple=8):
     return out
 
 
+def gather_layout(n_directions, world, bounds=None):
+    """Slices and row stride of the fused gather buffers float [world][F][per]: -> (bounds, per).
+
+    bounds: list of (d_begin, d_count) per rank tiling [0, D) in rank order (None: equal slices, shard_bounds).
+    per: the largest slice rounded up to 8 directions -- a warp stores its group of 8 values as ONE 32-byte write
+    per peer, which must not straddle two 32-byte sectors (equal slices of 4050 directions did: 100.2 k instead of
+    103.4 k maps/s on 8 GPUs)."""
+    if bounds is None:
+        bounds = [shard_bounds(n_directions, world, r)[1:] for r in range(world)]
+    bounds = [(int(b), int(c)) for b, c in bounds]
+    if len(bounds) != world or bounds[0][0] != 0 or any(c < 0 for _, c in bounds) or \
+            any(bounds[r][0] + bounds[r][1] != (bounds[r + 1][0] if r + 1 < world else n_directions)
+                for r in range(world)):
+        raise ValueError("PeerGather: bounds must tile [0, D) in rank order")
+    per = (max(c for _, c in bounds) + 7) // 8 * 8
+    return bounds, max(per, 8)
+
+
 class ShardedMaps:
     """maps = ShardedMaps(D, frames, rank, world, device); maps.compute(fn); maps.gather()
 
@@ -154,18 +172,8 @@ class PeerGather:
         from . import _native
         self.torch, self.nat, self.L = torch, _native, _native.lib()
         self.D, self.F, self.rank, self.world, self.depth = n_directions, frames, rank, world, depth
-        if bounds is None:
-            bounds = [shard_bounds(n_directions, world, r)[1:] for r in range(world)]
-        bounds = [(int(b), int(c)) for b, c in bounds]
-        if len(bounds) != world or bounds[0][0] != 0 or any(c < 0 for _, c in bounds) or \
-                any(bounds[r][0] + bounds[r][1] != (bounds[r + 1][0] if r + 1 < world else n_directions)
-                    for r in range(world)):
-            raise ValueError("PeerGather: bounds must tile [0, D) in rank order")
-        self.bounds = bounds
-        # row stride of a slice in the gather buffers: the largest slice, rounded up to 8 directions -- a warp stores
-        # its group of 8 values as ONE 32-byte write per peer, which must not straddle two 32-byte sectors (equal
-        # slices of 4050 directions did: 100.2 k instead of 103.4 k maps/s on 8 GPUs)
-        self.per = (max(c for _, c in bounds) + 7) // 8 * 8
+        self.bounds, self.per = gather_layout(n_directions, world, bounds)
+        bounds = self.bounds
         self.d_begin, self.d_count = bounds[rank]
         L = self.L
         vp = ctypes.c_void_p

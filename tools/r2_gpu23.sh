@@ -1,6 +1,8 @@
 #!/bin/bash
 # round-2 GPU call 23: tile hand-out A/B in one binary: BF_MIMO_SPLIT = 0 whole tiles (round 1), 1 frame-major unit ranges,
 # 2 full rounds + last round split into equal pieces
+# (mode 2 gained nothing and was removed after this call: the shipped library knows BF_MIMO_SPLIT = 0 / 1 only;
+# results in profiles/r2_kernel_variants.md)
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O

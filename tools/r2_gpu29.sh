@@ -1,5 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 29: uniform-pair handler (code 10: two uniform entries per dispatch) -- parity, then pairs on / off
+# (the pair handler lost 3.6 % and is a generator option only: BF_MIMO_PAIRS no longer exists in the library)
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O

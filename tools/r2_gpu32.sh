@@ -1,5 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 32: producer warp parked on its ring waits (try_wait with a suspend-time hint) instead of spinning
+# (no change measured; BF_MIMO_PARK_NS no longer exists in the library)
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O

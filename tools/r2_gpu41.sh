@@ -1,5 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 41: second half of the consumer warps one chunk behind the first (epilogues no longer coincide)
+# (no change measured; BF_MIMO_STAGGER no longer exists in the library)
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
